@@ -1,0 +1,96 @@
+/* libm3b200 -- C ABI of the B200-native VITS engine that replaces the
+ * onnxruntime.InferenceSession inside Mimic 3's Mimic3Voice.ids_to_audio.
+ *
+ * Plain C, plain pointers and sizes; no CUDA / torch types in any signature.
+ * Every entry point names the reference interface it replaces
+ * (paths relative to the MycroftAI/mimic3 checkout).
+ *
+ * Threading: one m3_voice may be shared by any number of host threads
+ * (like the shared ORT session, mimic3_tts/voice.py:277-292); m3_infer is
+ * re-entrant, weights are immutable, each call takes a private stream+workspace
+ * from a pool.  Errors never abort the process: a non-zero code is returned and
+ * m3_last_error() (thread-local) holds the message, which the Python wrapper turns
+ * into an exception the way ORT does (mimic3_http/synthesis.py:129-133).
+ */
+#ifndef M3B200_H_
+#define M3B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define M3_OK 0
+#define M3_ERR_INVALID 1 /* bad argument: id / sid out of range, bad shape (-> ValueError) */
+#define M3_ERR_IO 2      /* voice directory / file unreadable                               */
+#define M3_ERR_MODEL 3   /* generator.onnx / config.json inconsistent                       */
+#define M3_ERR_CUDA 4    /* CUDA runtime error                                              */
+#define M3_ERR_NOGPU 5   /* no usable sm_100 device: the engine has NO CPU fallback         */
+
+/* flags for m3_infer */
+#define M3_FLAG_KEEP_FLOAT 1u     /* also return the float32 waveform (ORT's "output")     */
+#define M3_FLAG_DEBUG_TENSORS 2u  /* keep named intermediates (tests only; slow)           */
+#define M3_FLAG_DEVICE_IDS 4u     /* `ids` is device memory already (benchmark "resident") */
+#define M3_FLAG_NO_HOST_COPY 8u   /* leave PCM on the device; host pointers are NULL       */
+
+typedef struct m3_voice m3_voice;   /* loaded voice == the ORT session object (voice.py:77,83) */
+typedef struct m3_result m3_result; /* one run's outputs == ORT's returned arrays             */
+
+typedef struct m3_voice_info {
+  int32_t num_symbols;     /* ModelConfig.num_symbols, mimic3_tts/config.py:116            */
+  int32_t n_speakers;      /* ModelConfig.n_speakers,  config.py:117                       */
+  int32_t is_multispeaker; /* TrainingConfig.is_multispeaker, config.py:316-318            */
+  int32_t has_speaker_embedding; /* emb_g present: "sid" is a graph input                  */
+  int32_t sample_rate;     /* AudioConfig.sample_rate, config.py:38                        */
+  int32_t hop_length;      /* product of upsample_rates (== AudioConfig.hop_length)        */
+  int32_t hidden_channels, inter_channels;
+  float noise_scale, length_scale, noise_w; /* InferenceConfig defaults, config.py:260-262 */
+  int64_t n_params;        /* fp32 parameters bound from generator.onnx                    */
+  int32_t device;          /* CUDA device ordinal the weights live on                      */
+  int32_t reserved;
+} m3_voice_info;
+
+const char* m3_version(void);
+/* Message of the last failing call on this thread ("" if none). */
+const char* m3_last_error(void);
+/* Number of visible CUDA devices with compute capability 10.x (0 => M3_ERR_NOGPU on load). */
+int32_t m3_device_count(void);
+
+/* Replaces Mimic3Voice._load_model: onnxruntime.InferenceSession(str(generator_path), ...)
+ * (mimic3_tts/voice.py:378-407).  `path` is the voice directory (config.json,
+ * generator.onnx -- voice.py:261,273) or the generator.onnx inside it. */
+int32_t m3_voice_load(const char* path, int32_t device, m3_voice** out);
+void m3_voice_free(m3_voice* voice);
+int32_t m3_voice_get_info(const m3_voice* voice, m3_voice_info* info);
+
+/* Replaces `self.onnx_model.run(None, inputs)` + `audio_float_to_int16`
+ * (mimic3_tts/voice.py:230-231, mimic3_tts/utils.py:237-244).
+ *   ids      int64 [batch][t_stride]  == inputs["input"]         (voice.py:180)
+ *   lengths  int64 [batch]            == inputs["input_lengths"] (voice.py:181)
+ *   scales   float [3] = {noise_scale, length_scale, noise_w}    (voice.py:182-189)
+ *   sid      int64 [batch] or NULL    == inputs["sid"]           (voice.py:217-218)
+ *   seed     selects the Philox noise stream (noise scales > 0 only)
+ * Every utterance is computed with batch-1 edge semantics (the reference never
+ * batches, voice.py:180-181) and is peak-normalised on its own. */
+int32_t m3_infer(m3_voice* voice, const int64_t* ids, const int64_t* lengths, int32_t batch, int32_t t_stride,
+                 const float* scales, const int64_t* sid, uint64_t seed, uint32_t flags, m3_result** out);
+
+int32_t m3_result_batch(const m3_result* r);
+/* sample_offsets[batch+1]: utterance b occupies [off[b], off[b+1]) of the packed buffers. */
+const int64_t* m3_result_sample_offsets(const m3_result* r);
+const int64_t* m3_result_num_frames(const m3_result* r);      /* [batch] mel frames (sum of durations) */
+const int16_t* m3_result_pcm(const m3_result* r);             /* packed int16, host (NULL with NO_HOST_COPY) */
+const float* m3_result_audio(const m3_result* r);             /* packed float32, host (KEEP_FLOAT only)      */
+const float* m3_result_peaks(const m3_result* r);             /* [batch] max|audio| per utterance            */
+const void* m3_result_device_pcm(const m3_result* r);         /* packed int16, device memory                 */
+double m3_result_device_ms(const m3_result* r);               /* GPU time of the call, CUDA events           */
+int64_t m3_result_kernel_launches(const m3_result* r);        /* kernels this call launched                  */
+/* Debug intermediates (M3_FLAG_DEBUG_TENSORS): row-major float [rows][cols]; returns M3_ERR_INVALID if absent. */
+int32_t m3_result_tensor(const m3_result* r, const char* name, const float** data, int64_t* rows, int64_t* cols);
+void m3_result_free(m3_result* r);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* M3B200_H_ */

@@ -1,0 +1,933 @@
+// Pipeline of one m3_infer call: TextEncoder -> duration predictor -> length regulator ->
+// coupling flow -> HiFi-GAN -> peak-normalised int16 (the ONNX graph
+// the reference runs at mimic3_tts/voice.py:230, plus utils.py:237-244).
+#include "engine.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "../../include/m3b200.h"
+#include "kernels.h"
+
+namespace m3 {
+
+// ======================================================================================
+// memory helpers
+// ======================================================================================
+void Arena::reserve(size_t bytes) {
+  used = 0;
+  if (bytes <= cap) return;
+  if (base) cudaFree(base);
+  base = nullptr;
+  cap = 0;
+  size_t want = bytes + bytes / 8 + (1 << 20);
+  M3_CUDA(cudaMalloc(&base, want));
+  cap = want;
+}
+Arena::~Arena() {
+  if (base) cudaFree(base);
+}
+void PinnedBuf::reserve(size_t bytes) {
+  if (bytes <= cap) return;
+  if (p) cudaFreeHost(p);
+  p = nullptr;
+  cap = 0;
+  size_t want = bytes + bytes / 8 + 4096;
+  M3_CUDA(cudaMallocHost(&p, want));
+  cap = want;
+}
+PinnedBuf::~PinnedBuf() {
+  if (p) cudaFreeHost(p);
+}
+Context::Context(int dev) : device(dev) {
+  M3_CUDA(cudaSetDevice(dev));
+  M3_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  M3_CUDA(cudaEventCreate(&ev0));
+  M3_CUDA(cudaEventCreate(&ev1));
+}
+Context::~Context() {
+  cudaSetDevice(device);
+  if (ev0) cudaEventDestroy(ev0);
+  if (ev1) cudaEventDestroy(ev1);
+  if (stream) cudaStreamDestroy(stream);
+}
+Context* Voice::acquire() {
+  std::lock_guard<std::mutex> lk(mu);
+  if (!idle.empty()) {
+    Context* c = idle.back();
+    idle.pop_back();
+    return c;
+  }
+  all.emplace_back(new Context(dv->device));
+  return all.back().get();
+}
+void Voice::release(Context* c) {
+  std::lock_guard<std::mutex> lk(mu);
+  idle.push_back(c);
+}
+DeviceVoice::~DeviceVoice() {
+  if (slab) {
+    cudaSetDevice(device);
+    cudaFree(slab);
+  }
+}
+
+// ======================================================================================
+// weight packing: PyTorch layouts -> channels-last GEMM operands, one device slab
+// ======================================================================================
+namespace {
+
+struct Packer {
+  std::vector<float> host;
+  size_t add(const std::vector<float>& v) {
+    size_t off = (host.size() + 63) & ~size_t(63);
+    host.resize(off + v.size());
+    std::copy(v.begin(), v.end(), host.begin() + off);
+    return off;
+  }
+};
+
+struct Pending {
+  const float** slot;
+  size_t off;
+};
+
+struct Builder {
+  const HostVoice& hv;
+  Packer pk;
+  std::vector<Pending> fix;
+  int64_t n_params = 0;
+  explicit Builder(const HostVoice& h) : hv(h) {}
+
+  void place(const float** slot, const std::vector<float>& v) { fix.push_back({slot, pk.add(v)}); }
+
+  // Conv1d weight (Cout, Cin, k) -> [k][Cin][Cout]
+  void conv(Lin& l, const std::string& base, int cout, int cin, int k, bool need_bias = true) {
+    const OnnxTensor& w = hv.need(base + ".weight", {cout, cin, k});
+    std::vector<float> t(size_t(k) * cin * cout);
+    for (int o = 0; o < cout; ++o)
+      for (int i = 0; i < cin; ++i)
+        for (int j = 0; j < k; ++j) t[(size_t(j) * cin + i) * cout + o] = w.f32[(size_t(o) * cin + i) * k + j];
+    place(&l.w, t);
+    n_params += int64_t(t.size());
+    l.cin = cin;
+    l.cout = cout;
+    l.taps = k;
+    l.b = nullptr;
+    if (const OnnxTensor* b = hv.maybe(base + ".bias")) {
+      if (b->numel() != cout) throw EngineError(3, "generator.onnx: '" + base + ".bias' has wrong size");
+      place(&l.b, b->f32);
+      n_params += cout;
+    } else if (need_bias) {
+      throw EngineError(3, "generator.onnx: missing initializer '" + base + ".bias'");
+    }
+  }
+  void vec(const float** slot, const std::string& name, int n) {
+    const OnnxTensor& t = hv.need(name, {});
+    if (t.numel() != n)
+      throw EngineError(3, "generator.onnx: '" + name + "' has " + std::to_string(t.numel()) + " elements, expected " +
+                               std::to_string(n));
+    place(slot, t.f32);
+    n_params += n;
+  }
+  void dds(DDSW& d, const std::string& p, int ch) {
+    for (int i = 0; i < 3; ++i) {
+      const std::string is = std::to_string(i);
+      const OnnxTensor& w = hv.need(p + ".convs_sep." + is + ".weight", {ch, 1, 3});
+      std::vector<float> t(size_t(3) * ch);
+      for (int c = 0; c < ch; ++c)
+        for (int j = 0; j < 3; ++j) t[size_t(j) * ch + c] = w.f32[size_t(c) * 3 + j];
+      place(&d.sep_w[i], t);
+      n_params += 3 * ch;
+      vec(&d.sep_b[i], p + ".convs_sep." + is + ".bias", ch);
+      conv(d.c1x1[i], p + ".convs_1x1." + is, ch, ch, 1);
+      vec(&d.n1g[i], p + ".norms_1." + is + ".gamma", ch);
+      vec(&d.n1b[i], p + ".norms_1." + is + ".beta", ch);
+      vec(&d.n2g[i], p + ".norms_2." + is + ".gamma", ch);
+      vec(&d.n2b[i], p + ".norms_2." + is + ".beta", ch);
+    }
+  }
+};
+
+}  // namespace
+
+std::unique_ptr<DeviceVoice> build_device_voice(const HostVoice& hv, int device) {
+  std::unique_ptr<DeviceVoice> dvp(new DeviceVoice());
+  DeviceVoice& dv = *dvp;
+  dv.cfg = hv.cfg;
+  dv.device = device;
+  const VoiceConfig& c = hv.cfg;
+  Builder B(hv);
+  const int H = c.hidden, I = c.inter, Ff = c.filter;
+  const int dk = H / c.n_heads;
+
+  // ---- text encoder
+  {
+    const OnnxTensor& e = hv.need("enc_p.emb.weight", {});
+    if (e.dims.size() != 2 || e.dims[1] != H)
+      throw EngineError(3, "generator.onnx: enc_p.emb.weight does not match hidden_channels");
+    if (c.num_symbols > 0 && e.dims[0] != c.num_symbols)
+      throw EngineError(3, "generator.onnx: enc_p.emb.weight rows != config.json model.num_symbols");
+    dv.cfg.num_symbols = int(e.dims[0]);
+    B.place(&dv.emb, e.f32);
+    B.n_params += e.numel();
+  }
+  dv.enc.resize(c.n_layers);
+  for (int l = 0; l < c.n_layers; ++l) {
+    EncLayerW& L = dv.enc[l];
+    const std::string a = "enc_p.encoder.attn_layers." + std::to_string(l);
+    {  // q | k | v concatenated along Cout
+      std::vector<float> w(size_t(H) * 3 * H), b(3 * H);
+      const char* names[3] = {".conv_q", ".conv_k", ".conv_v"};
+      for (int s = 0; s < 3; ++s) {
+        const OnnxTensor& t = hv.need(a + names[s] + ".weight", {H, H, 1});
+        const OnnxTensor& tb = hv.need(a + names[s] + ".bias", {H});
+        for (int o = 0; o < H; ++o) {
+          for (int i = 0; i < H; ++i) w[size_t(i) * 3 * H + s * H + o] = t.f32[size_t(o) * H + i];
+          b[s * H + o] = tb.f32[o];
+        }
+      }
+      B.place(&L.qkv.w, w);
+      B.place(&L.qkv.b, b);
+      L.qkv.cin = H;
+      L.qkv.cout = 3 * H;
+      L.qkv.taps = 1;
+      B.n_params += int64_t(w.size() + b.size());
+    }
+    B.conv(L.o, a + ".conv_o", H, H, 1);
+    {
+      const OnnxTensor& ek = hv.need(a + ".emb_rel_k", {});
+      const OnnxTensor& ev = hv.need(a + ".emb_rel_v", {});
+      if (ek.dims.size() != 3 || ek.dims[0] != 1 || ek.dims[2] != dk || ek.dims != ev.dims || (ek.dims[1] & 1) == 0)
+        throw EngineError(3, "generator.onnx: unexpected emb_rel_k/emb_rel_v shape (heads must share, odd window)");
+      dv.window = int(ek.dims[1] - 1) / 2;
+      B.place(&L.ek, ek.f32);
+      B.place(&L.ev, ev.f32);
+      B.n_params += 2 * ek.numel();
+    }
+    B.vec(&L.g1, "enc_p.encoder.norm_layers_1." + std::to_string(l) + ".gamma", H);
+    B.vec(&L.b1, "enc_p.encoder.norm_layers_1." + std::to_string(l) + ".beta", H);
+    B.vec(&L.g2, "enc_p.encoder.norm_layers_2." + std::to_string(l) + ".gamma", H);
+    B.vec(&L.b2, "enc_p.encoder.norm_layers_2." + std::to_string(l) + ".beta", H);
+    const std::string f = "enc_p.encoder.ffn_layers." + std::to_string(l);
+    B.conv(L.ffn1, f + ".conv_1", Ff, H, c.kernel_size);
+    B.conv(L.ffn2, f + ".conv_2", H, Ff, c.kernel_size);
+  }
+  B.conv(dv.enc_proj, "enc_p.proj", 2 * I, H, 1);
+
+  // ---- speaker embedding & conditioning layers (collected into one G -> n_cond GEMM)
+  const OnnxTensor* embg = hv.maybe("emb_g.weight");
+  dv.has_emb_g = embg != nullptr;
+  int G = 0;
+  if (embg) {
+    if (embg->dims.size() != 2) throw EngineError(3, "generator.onnx: emb_g.weight must be 2-D");
+    G = int(embg->dims[1]);
+    if (c.n_speakers > 1 && embg->dims[0] != c.n_speakers)
+      throw EngineError(3, "generator.onnx: emb_g.weight rows != config.json model.n_speakers");
+    dv.cfg.n_speakers = int(embg->dims[0]);
+    B.place(&dv.emb_g, embg->f32);
+    B.n_params += embg->numel();
+  }
+  std::vector<std::pair<std::string, int>> cond_layers;  // (module, width)
+  auto add_cond = [&](const std::string& mod, int width) -> int {
+    if (!G) return -1;
+    if (!hv.maybe(mod + ".weight")) return -1;
+    int off = 0;
+    for (auto& p : cond_layers) off += p.second;
+    cond_layers.emplace_back(mod, width);
+    return off;
+  };
+
+  // ---- duration predictor
+  dv.use_sdp = c.use_sdp && hv.maybe("dp.flows.0.m") != nullptr;
+  if (c.use_sdp && !dv.use_sdp && !hv.maybe("dp.conv_1.weight"))
+    throw EngineError(3, "generator.onnx: use_sdp is set but neither dp.flows.0.m nor dp.conv_1.weight exists");
+  if (dv.use_sdp) {
+    const int Fd = H;
+    dv.dp_ch = Fd;
+    B.conv(dv.dp_pre, "dp.pre", Fd, H, 1);
+    B.conv(dv.dp_proj, "dp.proj", Fd, Fd, 1);
+    B.dds(dv.dp_dds, "dp.convs", Fd);
+    dv.dp_cond_off = add_cond("dp.cond", Fd);
+    const OnnxTensor& m = hv.need("dp.flows.0.m", {2, 1});
+    const OnnxTensor& ls = hv.need("dp.flows.0.logs", {2, 1});
+    dv.ea_m[0] = m.f32[0]; dv.ea_m[1] = m.f32[1];
+    dv.ea_logs[0] = ls.f32[0]; dv.ea_logs[1] = ls.f32[1];
+    B.n_params += 4;
+    // flows = [EA, CF1, Flip, CF2, Flip, CF3, Flip, CF4, Flip]; reverse drops CF1 ("useless vflow")
+    for (int n : {7, 5, 3}) {
+      const std::string p = "dp.flows." + std::to_string(n);
+      dv.cflows.emplace_back();
+    }
+    int idx = 0;
+    for (int n : {7, 5, 3}) {
+      const std::string p = "dp.flows." + std::to_string(n);
+      ConvFlowW& cf = dv.cflows[idx++];
+      const OnnxTensor& pw = hv.need(p + ".pre.weight", {Fd, 1, 1});
+      B.place(&cf.pre_w, pw.f32);
+      B.vec(&cf.pre_b, p + ".pre.bias", Fd);
+      B.n_params += Fd;
+      B.dds(cf.dds, p + ".convs", Fd);
+      B.conv(cf.proj, p + ".proj", 29, Fd, 1);
+    }
+  } else {
+    const OnnxTensor& w1 = hv.need("dp.conv_1.weight", {});
+    if (w1.dims.size() != 3 || w1.dims[1] != H) throw EngineError(3, "generator.onnx: bad dp.conv_1.weight shape");
+    const int Fd = int(w1.dims[0]), k = int(w1.dims[2]);
+    dv.dp_ch = Fd;
+    B.conv(dv.dpp_c1, "dp.conv_1", Fd, H, k);
+    B.conv(dv.dpp_c2, "dp.conv_2", Fd, Fd, k);
+    B.conv(dv.dpp_proj, "dp.proj", 1, Fd, 1);
+    B.vec(&dv.dpp_g1, "dp.norm_1.gamma", Fd);
+    B.vec(&dv.dpp_b1, "dp.norm_1.beta", Fd);
+    B.vec(&dv.dpp_g2, "dp.norm_2.gamma", Fd);
+    B.vec(&dv.dpp_b2, "dp.norm_2.beta", Fd);
+    dv.dp_cond_off = add_cond("dp.cond", H);
+  }
+
+  // ---- flow (ResidualCouplingBlock): modules flows.{0,2,4,..}; applied in reverse
+  {
+    int nflows = 0;
+    while (hv.maybe("flow.flows." + std::to_string(2 * nflows) + ".pre.weight")) ++nflows;
+    if (!nflows) throw EngineError(3, "generator.onnx: no flow.flows.N.pre.weight found");
+    const OnnxTensor& pw = hv.need("flow.flows.0.pre.weight", {});
+    if (pw.dims.size() != 3 || pw.dims[1] != I / 2) throw EngineError(3, "generator.onnx: bad flow pre shape");
+    const int Hf = int(pw.dims[0]);
+    int nl = 0;
+    while (hv.maybe("flow.flows.0.enc.in_layers." + std::to_string(nl) + ".weight")) ++nl;
+    if (!nl) throw EngineError(3, "generator.onnx: flow WN in_layers missing (weight-norm not resolved?)");
+    const OnnxTensor& iw = hv.need("flow.flows.0.enc.in_layers.0.weight", {});
+    dv.flow_hidden = Hf;
+    dv.flow_layers = nl;
+    dv.flow_kernel = int(iw.dims[2]);
+    for (int f = nflows - 1; f >= 0; --f) {
+      const std::string p = "flow.flows." + std::to_string(2 * f);
+      dv.couplings.emplace_back();
+    }
+    int idx = 0;
+    for (int f = nflows - 1; f >= 0; --f) {
+      const std::string p = "flow.flows." + std::to_string(2 * f);
+      CouplingW& cw = dv.couplings[idx++];
+      B.conv(cw.pre, p + ".pre", Hf, I / 2, 1);
+      B.conv(cw.post, p + ".post", I / 2, Hf, 1);
+      cw.in.resize(nl);
+      cw.rs.resize(nl);
+      for (int i = 0; i < nl; ++i) {
+        B.conv(cw.in[i], p + ".enc.in_layers." + std::to_string(i), 2 * Hf, Hf, dv.flow_kernel);
+        B.conv(cw.rs[i], p + ".enc.res_skip_layers." + std::to_string(i), i < nl - 1 ? 2 * Hf : Hf, Hf, 1);
+      }
+      cw.cond_off = add_cond(p + ".enc.cond_layer", 2 * Hf * nl);
+    }
+  }
+
+  // ---- HiFi-GAN decoder
+  {
+    const int C0 = c.up_init;
+    B.conv(dv.dec_pre, "dec.conv_pre", C0, I, 7);
+    dv.dec_cond_off = add_cond("dec.cond", C0);
+    const int nk = int(c.rb_kernels.size());
+    dv.ups.resize(c.up_rates.size());
+    for (size_t i = 0; i < c.up_rates.size(); ++i) {
+      UpW& u = dv.ups[i];
+      u.cin = C0 >> i;
+      u.cout = C0 >> (i + 1);
+      u.k = c.up_kernels[i];
+      u.u = c.up_rates[i];
+      if ((u.k - u.u) < 0 || ((u.k - u.u) & 1))
+        throw EngineError(3, "config.json: upsample kernel/rate pair not supported (need k >= u, k-u even)");
+      u.pad = (u.k - u.u) / 2;
+      u.ntaps = (u.k + u.u - 1) / u.u;
+      const OnnxTensor& w = hv.need("dec.ups." + std::to_string(i) + ".weight", {u.cin, u.cout, u.k});
+      std::vector<float> t(size_t(u.u) * u.ntaps * u.cin * u.cout, 0.f);
+      for (int j1 = 0; j1 < u.u; ++j1)
+        for (int mp = 0; mp < u.ntaps; ++mp) {
+          const int m = u.ntaps - 1 - mp, j = j1 + m * u.u;
+          if (j >= u.k) continue;
+          for (int ci = 0; ci < u.cin; ++ci)
+            for (int co = 0; co < u.cout; ++co)
+              t[((size_t(j1) * u.ntaps + mp) * u.cin + ci) * u.cout + co] = w.f32[(size_t(ci) * u.cout + co) * u.k + j];
+        }
+      B.place(&u.w, t);
+      B.n_params += w.numel();
+      B.vec(&u.b, "dec.ups." + std::to_string(i) + ".bias", u.cout);
+      for (int j = 0; j < nk; ++j) {
+        ResBlockW rb;
+        rb.k = c.rb_kernels[j];
+        rb.dil = c.rb_dils[j];
+        const std::string rp = "dec.resblocks." + std::to_string(i * nk + j);
+        for (size_t d = 0; d < rb.dil.size(); ++d) {
+          Lin l1, l2;
+          if (c.resblock == "2") {
+            B.conv(l1, rp + ".convs." + std::to_string(d), u.cout, u.cout, rb.k);
+            rb.c1.push_back(l1);
+          } else {
+            B.conv(l1, rp + ".convs1." + std::to_string(d), u.cout, u.cout, rb.k);
+            B.conv(l2, rp + ".convs2." + std::to_string(d), u.cout, u.cout, rb.k);
+            rb.c1.push_back(l1);
+            rb.c2.push_back(l2);
+          }
+        }
+        dv.rbs.push_back(rb);
+      }
+    }
+    const int cl = C0 >> c.up_rates.size();
+    const OnnxTensor& pw = hv.need("dec.conv_post.weight", {});
+    if (pw.dims.size() != 3 || pw.dims[0] != 1 || pw.dims[1] != cl)
+      throw EngineError(3, "generator.onnx: bad dec.conv_post.weight shape");
+    dv.post_k = int(pw.dims[2]);
+    dv.post_c = cl;
+    std::vector<float> t(size_t(dv.post_k) * cl);
+    for (int ci = 0; ci < cl; ++ci)
+      for (int j = 0; j < dv.post_k; ++j) t[size_t(j) * cl + ci] = pw.f32[size_t(ci) * dv.post_k + j];
+    B.place(&dv.post_w, t);
+    B.n_params += pw.numel();
+  }
+
+  // ---- conditioning GEMM [G][n_cond]
+  if (G && !cond_layers.empty()) {
+    int n = 0;
+    for (auto& p : cond_layers) n += p.second;
+    dv.n_cond = n;
+    std::vector<float> w(size_t(G) * n), b(n);
+    int off = 0;
+    for (auto& p : cond_layers) {
+      const OnnxTensor& t = hv.need(p.first + ".weight", {p.second, G, 1});
+      const OnnxTensor& tb = hv.need(p.first + ".bias", {p.second});
+      for (int o = 0; o < p.second; ++o) {
+        for (int g = 0; g < G; ++g) w[size_t(g) * n + off + o] = t.f32[size_t(o) * G + g];
+        b[off + o] = tb.f32[o];
+      }
+      off += p.second;
+      B.n_params += t.numel() + tb.numel();
+    }
+    B.place(&dv.cond_all.w, w);
+    B.place(&dv.cond_all.b, b);
+    dv.cond_all.cin = G;
+    dv.cond_all.cout = n;
+    dv.cond_all.taps = 1;
+  }
+  dv.cfg.gin = G;
+
+  // ---- upload (everything above is host-only, so model errors surface without a GPU)
+  {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+      cudaGetLastError();
+      throw EngineError(M3_ERR_NOGPU, "no CUDA device visible: libm3b200 has no CPU fallback");
+    }
+    if (device < 0 || device >= n) throw EngineError(M3_ERR_INVALID, "device ordinal out of range");
+    int major = 0;
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device);
+    if (major != 10)
+      throw EngineError(M3_ERR_NOGPU, "device " + std::to_string(device) + " is compute capability " +
+                                          std::to_string(major) + ".x; this library carries sm_100a code only");
+  }
+  M3_CUDA(cudaSetDevice(device));
+  dv.slab_floats = B.pk.host.size();
+  M3_CUDA(cudaMalloc(&dv.slab, dv.slab_floats * sizeof(float)));
+  M3_CUDA(cudaMemcpy(dv.slab, B.pk.host.data(), dv.slab_floats * sizeof(float), cudaMemcpyHostToDevice));
+  for (auto& f : B.fix) *f.slot = dv.slab + f.off;
+  dv.n_params = B.n_params;
+  return dvp;
+}
+
+// ======================================================================================
+// the pipeline
+// ======================================================================================
+namespace {
+
+struct Segs {
+  const int* off;
+  const int* len;
+  int n;
+  int max_len;
+};
+
+struct Run {
+  DeviceVoice& dv;
+  Context& cx;
+  cudaStream_t st;
+  Result* res;
+  bool debug;
+
+  ConvParams base_conv(const Lin& l, const float* in, int in_stride, float* out, int out_stride, const Segs& s,
+                       int scale) const {
+    ConvParams p;
+    p.in = in;
+    p.in_stride = in_stride;
+    p.Cin = l.cin;
+    p.W = l.w;
+    p.Cout = l.cout;
+    p.taps = l.taps;
+    p.pad_left = (l.taps - 1) / 2;
+    p.bias = l.b;
+    p.out = out;
+    p.out_stride = out_stride;
+    p.seg_off = s.off;
+    p.seg_len = s.len;
+    p.in_scale = scale;
+    p.out_scale = scale;
+    return p;
+  }
+  void conv(const ConvParams& p, const Segs& s) const { launch_conv(p, s.n, s.max_len, st); }
+
+  void dump(const char* name, const float* d, int64_t rows, int64_t cols) const {
+    if (!debug) return;
+    DebugTensor t;
+    t.rows = rows;
+    t.cols = cols;
+    t.data.resize(size_t(rows * cols));
+    M3_CUDA(cudaStreamSynchronize(st));
+    M3_CUDA(cudaMemcpy(t.data.data(), d, t.data.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    res->debug[name] = std::move(t);
+  }
+
+  // DDSConv (modules.DDSConv [EXT]): x updated in place; tmp1/tmp2 scratch [rows][C]
+  void dds(const DDSW& d, float* x, float* tmp1, float* tmp2, int C, const Segs& s, int rows) const {
+    int dil = 1;
+    for (int i = 0; i < 3; ++i) {
+      launch_dds_sep(x, d.sep_w[i], d.sep_b[i], d.n1g[i], d.n1b[i], tmp1, C, dil, s.off, s.len, s.n, s.max_len, st);
+      ConvParams p = base_conv(d.c1x1[i], tmp1, C, tmp2, C, s, 1);
+      conv(p, s);
+      launch_layernorm(tmp2, nullptr, x, d.n2g[i], d.n2b[i], x, rows, C, 1, st);
+      dil *= 3;
+    }
+  }
+};
+
+}  // namespace
+
+Result* run_inference(Voice& v, const int64_t* ids, const int64_t* lengths, int batch, int t_stride,
+                      const float* scales, const int64_t* sid, uint64_t seed, uint32_t flags) {
+  DeviceVoice& dv = *v.dv;
+  const VoiceConfig& c = dv.cfg;
+  if (batch <= 0) throw EngineError(M3_ERR_INVALID, "batch must be >= 1");
+  if (!ids || !lengths || !scales) throw EngineError(M3_ERR_INVALID, "ids, lengths and scales must not be NULL");
+  if (t_stride <= 0) throw EngineError(M3_ERR_INVALID, "input has zero phonemes");
+  if (dv.has_emb_g && !sid) throw EngineError(M3_ERR_INVALID, "multi-speaker voice: input 'sid' is required");
+  const float noise_scale = scales[0], length_scale = scales[1], noise_w = scales[2];
+  const bool ids_on_device = flags & M3_FLAG_DEVICE_IDS;
+
+  std::vector<int> tok_off(batch), tok_len(batch);
+  int NT = 0, Tmax = 0;
+  for (int b = 0; b < batch; ++b) {
+    if (lengths[b] <= 0 || lengths[b] > t_stride)
+      throw EngineError(M3_ERR_INVALID, "input_lengths[" + std::to_string(b) + "]=" + std::to_string(lengths[b]) +
+                                            " outside [1, " + std::to_string(t_stride) + "]");
+    tok_off[b] = NT;
+    tok_len[b] = int(lengths[b]);
+    NT += tok_len[b];
+    Tmax = std::max(Tmax, tok_len[b]);
+  }
+  if (sid && dv.has_emb_g)
+    for (int b = 0; b < batch; ++b)
+      if (sid[b] < 0 || sid[b] >= c.n_speakers)
+        throw EngineError(M3_ERR_INVALID, "sid[" + std::to_string(b) + "]=" + std::to_string(sid[b]) +
+                                              " outside [0, " + std::to_string(c.n_speakers) + ")");
+  if (!ids_on_device)
+    for (int b = 0; b < batch; ++b)
+      for (int t = 0; t < tok_len[b]; ++t) {
+        const int64_t id = ids[size_t(b) * t_stride + t];
+        if (id < 0 || id >= c.num_symbols)
+          throw EngineError(M3_ERR_INVALID, "input[" + std::to_string(b) + "][" + std::to_string(t) + "]=" +
+                                                std::to_string(id) + " outside [0, " + std::to_string(c.num_symbols) + ")");
+      }
+
+  M3_CUDA(cudaSetDevice(dv.device));
+  Context* cxp = v.acquire();
+  std::unique_ptr<Result> res(new Result());
+  res->batch = batch;
+  res->owner = &v;
+  res->ctx = cxp;
+  struct Lease {
+    Voice& v;
+    Context* c;
+    bool keep = false;
+    ~Lease() {
+      if (!keep) v.release(c);
+    }
+  } lease{v, cxp};
+  Context& cx = *cxp;
+  cudaStream_t st = cx.stream;
+  g_launch_count = 0;
+  Run R{dv, cx, st, res.get(), (flags & M3_FLAG_DEBUG_TENSORS) != 0};
+
+  const int H = c.hidden, I = c.inter, Ff = c.filter, Fd = dv.dp_ch;
+  const int G = c.gin;
+
+  // ---------------- phase 1 workspace (token level) ----------------
+  {
+    size_t fl = size_t(NT) * (size_t(H) * 3 + 3 * H + Ff + 2 * I + size_t(Fd) * 4 + 40) + size_t(batch) * (G + dv.n_cond + 8);
+    size_t bytes = fl * 4 + size_t(batch) * t_stride * 8 + size_t(batch) * 64 + (1 << 16) + 512 * 64;
+    cx.a1.reserve(bytes);
+  }
+  Arena& A = cx.a1;
+  int* d_meta = A.alloc<int>(size_t(batch) * 4 + 4);  // tok_off | tok_len | frm_off | frm_len
+  int* d_tok_off = d_meta;
+  int* d_tok_len = d_meta + batch;
+  int* d_frm_off = d_meta + 2 * batch;
+  int* d_frm_len = d_meta + 3 * batch;
+  int64_t* d_ids = nullptr;
+  int64_t* d_sid = A.alloc<int64_t>(batch);
+  int* d_one = A.alloc<int>(4);  // {0, batch}: a single segment of `batch` rows
+
+  // stage host inputs in pinned memory, one async copy each
+  cx.h_meta.reserve(size_t(batch) * 4 * sizeof(int) + size_t(batch) * 8 + 64);
+  int* hm = static_cast<int*>(cx.h_meta.p);
+  memcpy(hm, tok_off.data(), batch * sizeof(int));
+  memcpy(hm + batch, tok_len.data(), batch * sizeof(int));
+  M3_CUDA(cudaEventRecord(cx.ev0, st));
+  M3_CUDA(cudaMemcpyAsync(d_meta, hm, size_t(batch) * 2 * sizeof(int), cudaMemcpyHostToDevice, st));
+  {
+    int* ho = hm + 4 * batch;
+    ho[0] = 0;
+    ho[1] = batch;
+    M3_CUDA(cudaMemcpyAsync(d_one, ho, 2 * sizeof(int), cudaMemcpyHostToDevice, st));
+  }
+  if (ids_on_device) {
+    d_ids = const_cast<int64_t*>(ids);
+  } else {
+    d_ids = A.alloc<int64_t>(size_t(batch) * t_stride);
+    cx.h_in.reserve(size_t(batch) * t_stride * 8);
+    memcpy(cx.h_in.p, ids, size_t(batch) * t_stride * 8);
+    M3_CUDA(cudaMemcpyAsync(d_ids, cx.h_in.p, size_t(batch) * t_stride * 8, cudaMemcpyHostToDevice, st));
+  }
+  Segs tok{d_tok_off, d_tok_len, batch, Tmax};
+  Segs one{d_one, d_one + 1, 1, batch};
+
+  // ---------------- speaker conditioning ----------------
+  float* d_cond = nullptr;  // [batch][n_cond]
+  if (dv.has_emb_g && dv.n_cond) {
+    int64_t* hs = reinterpret_cast<int64_t*>(hm + 4 * batch + 8);
+    memcpy(hs, sid, size_t(batch) * 8);
+    M3_CUDA(cudaMemcpyAsync(d_sid, hs, size_t(batch) * 8, cudaMemcpyHostToDevice, st));
+    float* d_g = A.alloc<float>(size_t(batch) * G);
+    d_cond = A.alloc<float>(size_t(batch) * dv.n_cond);
+    launch_gather_rows(d_sid, dv.emb_g, d_g, batch, G, st);
+    ConvParams p = R.base_conv(dv.cond_all, d_g, G, d_cond, dv.n_cond, one, 1);
+    R.conv(p, one);
+  }
+  auto ubias = [&](int off) -> const float* { return (d_cond && off >= 0) ? d_cond + off : nullptr; };
+
+  // ---------------- A.1 text encoder ----------------
+  float* x = A.alloc<float>(size_t(NT) * H);
+  float* qkv = A.alloc<float>(size_t(NT) * 3 * H);
+  float* att = A.alloc<float>(size_t(NT) * H);
+  float* y = A.alloc<float>(size_t(NT) * H);
+  float* ffn = A.alloc<float>(size_t(NT) * Ff);
+  float* stats = A.alloc<float>(size_t(NT) * 2 * I);
+  launch_embedding(d_ids, t_stride, dv.emb, c.num_symbols, sqrtf(float(H)), x, H, d_tok_off, d_tok_len, batch, Tmax, st);
+  for (int l = 0; l < c.n_layers; ++l) {
+    const EncLayerW& L = dv.enc[l];
+    R.conv(R.base_conv(L.qkv, x, H, qkv, 3 * H, tok, 1), tok);
+    launch_attention(qkv, L.ek, L.ev, att, H, c.n_heads, dv.window, d_tok_off, d_tok_len, batch, Tmax, st);
+    R.conv(R.base_conv(L.o, att, H, y, H, tok, 1), tok);
+    launch_layernorm(x, y, nullptr, L.g1, L.b1, x, NT, H, 0, st);
+    {
+      ConvParams p = R.base_conv(L.ffn1, x, H, ffn, Ff, tok, 1);
+      p.act = 1;
+      R.conv(p, tok);
+      // attentions.FFN "same" padding: pad_l = (k-1)//2, pad_r = k//2  -> pad_left as base_conv
+    }
+    R.conv(R.base_conv(L.ffn2, ffn, Ff, y, H, tok, 1), tok);
+    launch_layernorm(x, y, nullptr, L.g2, L.b2, x, NT, H, 0, st);
+  }
+  R.conv(R.base_conv(dv.enc_proj, x, H, stats, 2 * I, tok, 1), tok);
+  R.dump("x", x, NT, H);
+  R.dump("stats", stats, NT, 2 * I);
+
+  // ---------------- A.2 duration predictor ----------------
+  float* logw = A.alloc<float>(NT);
+  if (dv.use_sdp) {
+    float* h = A.alloc<float>(size_t(NT) * Fd);
+    float* u = A.alloc<float>(size_t(NT) * Fd);
+    float* t1 = A.alloc<float>(size_t(NT) * Fd);
+    float* t2 = A.alloc<float>(size_t(NT) * Fd);
+    float* pr = A.alloc<float>(size_t(NT) * 32);
+    float* z = A.alloc<float>(size_t(NT) * 2);
+    {
+      ConvParams p = R.base_conv(dv.dp_pre, x, H, h, Fd, tok, 1);
+      p.ubias = ubias(dv.dp_cond_off);
+      p.ub_stride = dv.n_cond;
+      R.conv(p, tok);
+    }
+    R.dds(dv.dp_dds, h, t1, t2, Fd, tok, NT);
+    R.conv(R.base_conv(dv.dp_proj, h, Fd, t1, Fd, tok, 1), tok);
+    float* hc = t1;  // conditioning for the conv flows
+    float* s1 = h;   // h is free now: reuse as scratch
+    launch_sdp_noise(z, noise_w, seed, d_tok_off, d_tok_len, batch, Tmax, st);
+    // z channels are never moved: `c0` tracks which physical column is logical channel 0
+    int c0 = 0;
+    const float inv_sqrt = 1.0f / sqrtf(float(Fd));
+    for (size_t f = 0; f < dv.cflows.size(); ++f) {
+      c0 ^= 1;  // Flip
+      const ConvFlowW& cf = dv.cflows[f];
+      launch_convflow_pre(z, c0, cf.pre_w, cf.pre_b, hc, u, NT, Fd, st);
+      R.dds(cf.dds, u, s1, t2, Fd, tok, NT);
+      R.conv(R.base_conv(cf.proj, u, Fd, pr, 32, tok, 1), tok);
+      launch_rqs_inverse(z, c0 ^ 1, pr, 32, inv_sqrt, NT, st);
+    }
+    c0 ^= 1;  // final Flip, then ElementwiseAffine^-1; logw = logical channel 0
+    launch_sdp_finish(z, c0, dv.ea_m[0], dv.ea_logs[0], logw, NT, st);
+  } else {
+    float* h = A.alloc<float>(size_t(NT) * std::max(Fd, H));
+    float* h2 = A.alloc<float>(size_t(NT) * Fd);
+    const float* xin = x;
+    if (const float* ub = ubias(dv.dp_cond_off)) {  // x = x + cond(g)
+      launch_add_ubias(x, ub, dv.n_cond, h, H, d_tok_off, d_tok_len, batch, Tmax, st);
+      xin = h;
+    }
+    {
+      ConvParams p = R.base_conv(dv.dpp_c1, xin, H, h2, Fd, tok, 1);
+      p.act = 1;
+      R.conv(p, tok);
+    }
+    launch_layernorm(h2, nullptr, nullptr, dv.dpp_g1, dv.dpp_b1, h2, NT, Fd, 0, st);
+    float* h3 = A.alloc<float>(size_t(NT) * Fd);
+    {
+      ConvParams p = R.base_conv(dv.dpp_c2, h2, Fd, h3, Fd, tok, 1);
+      p.act = 1;
+      R.conv(p, tok);
+    }
+    launch_layernorm(h3, nullptr, nullptr, dv.dpp_g2, dv.dpp_b2, h3, NT, Fd, 0, st);
+    R.conv(R.base_conv(dv.dpp_proj, h3, Fd, logw, 1, tok, 1), tok);
+  }
+  R.dump("logw", logw, NT, 1);
+
+  // ---------------- A.0 durations -> frames ----------------
+  int* cum = A.alloc<int>(NT);
+  launch_durations(logw, 1, length_scale, cum, d_frm_len, d_tok_off, d_tok_len, batch, st);
+  int* h_frames = hm + 2 * batch;
+  M3_CUDA(cudaMemcpyAsync(h_frames, d_frm_len, size_t(batch) * sizeof(int), cudaMemcpyDeviceToHost, st));
+  M3_CUDA(cudaStreamSynchronize(st));
+  std::vector<int> frm_off(batch), frm_len(batch);
+  int64_t NF = 0;
+  int Fmax = 0;
+  for (int b = 0; b < batch; ++b) {
+    frm_len[b] = h_frames[b];
+    frm_off[b] = int(NF);
+    NF += frm_len[b];
+    Fmax = std::max(Fmax, frm_len[b]);
+  }
+  const int hop = c.hop();
+  if (NF * hop > (int64_t(1) << 31) - 1)
+    throw EngineError(M3_ERR_INVALID, "batch produces more than 2^31 samples; split the batch");
+  res->frames.assign(frm_len.begin(), frm_len.end());
+  res->sample_off.resize(batch + 1);
+  for (int b = 0; b < batch; ++b) res->sample_off[b] = int64_t(frm_off[b]) * hop;
+  res->sample_off[batch] = NF * hop;
+  memcpy(hm + 2 * batch, frm_off.data(), batch * sizeof(int));
+  memcpy(hm + 3 * batch, frm_len.data(), batch * sizeof(int));
+  M3_CUDA(cudaMemcpyAsync(d_frm_off, hm + 2 * batch, size_t(batch) * 2 * sizeof(int), cudaMemcpyHostToDevice, st));
+  Segs frm{d_frm_off, d_frm_len, batch, Fmax};
+  if (R.debug) {
+    DebugTensor t;
+    t.rows = NT;
+    t.cols = 1;
+    std::vector<int> hc(NT);
+    M3_CUDA(cudaMemcpy(hc.data(), cum, size_t(NT) * 4, cudaMemcpyDeviceToHost));
+    t.data.resize(NT);
+    for (int b = 0; b < batch; ++b)
+      for (int t2 = 0; t2 < tok_len[b]; ++t2) {
+        const int i = tok_off[b] + t2;
+        t.data[i] = float(hc[i] - (t2 ? hc[i - 1] : 0));
+      }
+    res->debug["durations"] = std::move(t);
+  }
+
+  // ---------------- phase 2 workspace (frame level) ----------------
+  const int Hf = dv.flow_hidden;
+  const int C0 = c.up_init;
+  {
+    size_t fl = size_t(NF) * (size_t(I) + 3 * size_t(Hf) + C0);
+    int scale = 1;
+    for (size_t i = 0; i < dv.ups.size(); ++i) {
+      scale *= dv.ups[i].u;
+      fl += size_t(NF) * scale * dv.ups[i].cout * 5;  // x, y0, y1, tmp, sum
+    }
+    fl += size_t(NF) * hop;                 // audio
+    size_t bytes = fl * 4 + size_t(NF) * hop * 2 + size_t(batch) * 16 + (1 << 16) + 512 * 64;
+    cx.a2.reserve(bytes);
+  }
+  Arena& A2 = cx.a2;
+
+  // ---------------- length regulator + prior sample ----------------
+  float* z = A2.alloc<float>(size_t(NF) * I);
+  launch_expand(stats, I, cum, d_tok_off, d_tok_len, d_frm_off, d_frm_len, batch, Fmax, noise_scale, seed, z, st);
+  R.dump("z_p", z, NF, I);
+
+  // ---------------- A.3 flow (reverse) ----------------
+  {
+    float* h = A2.alloc<float>(size_t(NF) * Hf);
+    float* act = A2.alloc<float>(size_t(NF) * Hf);
+    float* skip = A2.alloc<float>(size_t(NF) * Hf);
+    const int half = I / 2;
+    for (size_t f = 0; f < dv.couplings.size(); ++f) {
+      const CouplingW& cw = dv.couplings[f];
+      launch_flip_channels(z, int(NF), I, st);
+      R.conv(R.base_conv(cw.pre, z, I, h, Hf, frm, 1), frm);  // x0 = z[:, :half]
+      M3_CUDA(cudaMemsetAsync(skip, 0, size_t(NF) * Hf * 4, st));
+      const int nl = dv.flow_layers;
+      for (int i = 0; i < nl; ++i) {
+        {
+          ConvParams p = R.base_conv(cw.in[i], h, Hf, act, Hf, frm, 1);
+          p.Cout = Hf;
+          p.gate = 1;
+          if (const float* ub = ubias(cw.cond_off)) {
+            p.ubias = ub + size_t(i) * 2 * Hf;
+            p.ub_stride = dv.n_cond;
+          }
+          R.conv(p, frm);
+        }
+        {
+          ConvParams p = R.base_conv(cw.rs[i], act, Hf, h, Hf, frm, 1);
+          p.mode = 1;
+          if (i < nl - 1) {
+            p.split = Hf;
+            p.out2 = skip;
+            p.out2_stride = Hf;
+          } else {
+            p.out = skip;
+            p.out_stride = Hf;
+          }
+          R.conv(p, frm);
+        }
+      }
+      {
+        ConvParams p = R.base_conv(cw.post, skip, Hf, z, I, frm, 1);
+        p.out_coff = half;
+        p.mode = 2;  // x1 = x1 - m   (mean_only coupling)
+        R.conv(p, frm);
+      }
+    }
+  }
+  R.dump("z", z, NF, I);
+
+  // ---------------- A.4 HiFi-GAN ----------------
+  float* cur = A2.alloc<float>(size_t(NF) * C0);
+  {
+    ConvParams p = R.base_conv(dv.dec_pre, z, I, cur, C0, frm, 1);
+    if (const float* ub = ubias(dv.dec_cond_off)) {
+      p.ubias = ub;
+      p.ub_stride = dv.n_cond;
+    }
+    R.conv(p, frm);
+  }
+  int scale = 1;
+  const int nk = int(c.rb_kernels.size());
+  for (size_t i = 0; i < dv.ups.size(); ++i) {
+    const UpW& u = dv.ups[i];
+    const int out_scale = scale * u.u;
+    const size_t n = size_t(NF) * out_scale * u.cout;
+    float* xu = A2.alloc<float>(n);
+    float* yb[2] = {A2.alloc<float>(n), A2.alloc<float>(n)};
+    float* tb = A2.alloc<float>(n);
+    float* sum = A2.alloc<float>(n);
+    {
+      ConvParams p;
+      p.in = cur;
+      p.in_stride = u.cin;
+      p.Cin = u.cin;
+      p.in_slope = 0.1f;
+      p.W = u.w;
+      p.w_phase_stride = (long long)u.ntaps * u.cin * u.cout;
+      p.Cout = u.cout;
+      p.taps = u.ntaps;
+      p.pad_left = u.ntaps - 1;
+      p.bias = u.b;
+      p.out = xu;
+      p.out_stride = u.cout;
+      p.seg_off = d_frm_off;
+      p.seg_len = d_frm_len;
+      p.in_scale = scale;
+      p.out_scale = out_scale;
+      p.rows_extra = u.ntaps - 1;
+      p.out_mul = u.u;
+      p.out_add = -u.pad;
+      p.out_add_phase = 1;
+      p.phases = u.u;
+      launch_conv(p, batch, Fmax, st);
+    }
+    Segs lvl{d_frm_off, d_frm_len, batch, Fmax};
+    for (int j = 0; j < nk; ++j) {
+      const ResBlockW& rb = dv.rbs[i * nk + j];
+      const float* src = xu;
+      const size_t nd = rb.dil.size();
+      for (size_t d = 0; d < nd; ++d) {
+        const bool last = d + 1 == nd;
+        if (rb.c2.empty()) {  // ResBlock2: x = x + conv_d(lrelu(x))
+          ConvParams p = R.base_conv(rb.c1[d], src, u.cout, last ? sum : yb[d & 1], u.cout, lvl, out_scale);
+          p.dil = rb.dil[d];
+          p.pad_left = (rb.k - 1) / 2;  // in taps; the kernel multiplies by the dilation
+          p.in_slope = 0.1f;
+          p.res = src;
+          p.res_stride = u.cout;
+          if (last) {
+            p.scale = 1.0f / float(nk);
+            p.mode = j == 0 ? 0 : 1;
+          }
+          R.conv(p, lvl);
+        } else {  // ResBlock1: t = conv1_d(lrelu(x)); t = conv2(lrelu(t)); x = x + t
+          {
+            ConvParams p = R.base_conv(rb.c1[d], src, u.cout, tb, u.cout, lvl, out_scale);
+            p.dil = rb.dil[d];
+            p.pad_left = (rb.k - 1) / 2;
+            p.in_slope = 0.1f;
+            R.conv(p, lvl);
+          }
+          {
+            ConvParams p = R.base_conv(rb.c2[d], tb, u.cout, last ? sum : yb[d & 1], u.cout, lvl, out_scale);
+            p.pad_left = (rb.k - 1) / 2;
+            p.in_slope = 0.1f;
+            p.res = src;
+            p.res_stride = u.cout;
+            if (last) {
+              p.scale = 1.0f / float(nk);
+              p.mode = j == 0 ? 0 : 1;
+            }
+            R.conv(p, lvl);
+          }
+        }
+        src = yb[d & 1];
+      }
+    }
+    cur = sum;
+    scale = out_scale;
+    if (i == 0) R.dump("mrf0", sum, NF * out_scale, u.cout);
+  }
+  float* audio = A2.alloc<float>(size_t(NF) * hop);
+  int16_t* pcm = A2.alloc<int16_t>(size_t(NF) * hop);
+  unsigned* peak = A2.alloc<unsigned>(batch);
+  M3_CUDA(cudaMemsetAsync(peak, 0, size_t(batch) * 4, st));
+  launch_conv_post(cur, dv.post_c, dv.post_w, dv.post_k, 0.01f, audio, peak, d_frm_off, d_frm_len, hop, batch, Fmax, st);
+  launch_to_int16(audio, peak, pcm, d_frm_off, d_frm_len, hop, batch, Fmax, st);
+
+  // ---------------- outputs ----------------
+  const size_t NS = size_t(NF) * hop;
+  res->d_pcm = pcm;
+  float* h_peaks = reinterpret_cast<float*>(hm);  // reuse meta staging (tok arrays no longer needed on host)
+  M3_CUDA(cudaMemcpyAsync(h_peaks, peak, size_t(batch) * 4, cudaMemcpyDeviceToHost, st));
+  if (!(flags & M3_FLAG_NO_HOST_COPY)) {
+    cx.h_pcm.reserve(NS * 2);
+    M3_CUDA(cudaMemcpyAsync(cx.h_pcm.p, pcm, NS * 2, cudaMemcpyDeviceToHost, st));
+    res->pcm = static_cast<const int16_t*>(cx.h_pcm.p);
+    if (flags & M3_FLAG_KEEP_FLOAT) {
+      cx.h_audio.reserve(NS * 4);
+      M3_CUDA(cudaMemcpyAsync(cx.h_audio.p, audio, NS * 4, cudaMemcpyDeviceToHost, st));
+      res->audio = static_cast<const float*>(cx.h_audio.p);
+    }
+  }
+  M3_CUDA(cudaEventRecord(cx.ev1, st));
+  M3_CUDA(cudaStreamSynchronize(st));
+  M3_CUDA(cudaGetLastError());
+  float ms = 0;
+  M3_CUDA(cudaEventElapsedTime(&ms, cx.ev0, cx.ev1));
+  res->device_ms = ms;
+  res->launches = g_launch_count;
+  res->peaks.assign(h_peaks, h_peaks + batch);
+  lease.keep = true;
+  return res.release();
+}
+
+}  // namespace m3

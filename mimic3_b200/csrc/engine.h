@@ -1,0 +1,177 @@
+// Engine internals shared by engine.cu and m3_api.cc.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <condition_variable>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "voice_model.h"
+
+namespace m3 {
+
+struct EngineError : std::runtime_error {
+  int code;
+  EngineError(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define M3_CUDA(expr)                                                                                   \
+  do {                                                                                                  \
+    cudaError_t _e = (expr);                                                                            \
+    if (_e != cudaSuccess)                                                                              \
+      throw ::m3::EngineError(4, std::string("CUDA error: ") + cudaGetErrorString(_e) + " at " #expr); \
+  } while (0)
+
+struct Lin {  // a Conv1d packed as [taps][Cin][ldw] (+ bias[ldw])
+  const float* w = nullptr;
+  const float* b = nullptr;
+  int cin = 0, cout = 0, taps = 1;
+};
+
+struct DDSW {
+  const float* sep_w[3];
+  const float* sep_b[3];
+  Lin c1x1[3];
+  const float *n1g[3], *n1b[3], *n2g[3], *n2b[3];
+};
+
+struct EncLayerW {
+  Lin qkv, o, ffn1, ffn2;
+  const float *ek, *ev, *g1, *b1, *g2, *b2;
+};
+
+struct ConvFlowW {
+  const float *pre_w, *pre_b;
+  DDSW dds;
+  Lin proj;
+};
+
+struct CouplingW {
+  Lin pre, post;
+  std::vector<Lin> in, rs;
+  int cond_off = -1;
+};
+
+struct UpW {
+  const float* w = nullptr;  // [phase u][ntaps][Cin][Cout]
+  const float* b = nullptr;
+  int cin = 0, cout = 0, k = 0, u = 0, ntaps = 0, pad = 0;
+};
+
+struct ResBlockW {
+  int k = 0;
+  std::vector<int> dil;
+  std::vector<Lin> c1, c2;  // c2 empty for resblock "2"
+};
+
+struct DeviceVoice {
+  VoiceConfig cfg;
+  int device = 0;
+  float* slab = nullptr;  // all weights, one allocation
+  size_t slab_floats = 0;
+  int64_t n_params = 0;
+  bool has_emb_g = false;
+  int window = 4;
+
+  const float* emb = nullptr;
+  std::vector<EncLayerW> enc;
+  Lin enc_proj;
+  // duration predictor
+  bool use_sdp = true;
+  int dp_ch = 0;
+  Lin dp_pre, dp_proj;
+  DDSW dp_dds;
+  float ea_m[2] = {0, 0}, ea_logs[2] = {0, 0};
+  std::vector<ConvFlowW> cflows;  // in application order (flows.7, .5, .3)
+  Lin dpp_c1, dpp_c2, dpp_proj;   // plain DurationPredictor
+  const float *dpp_g1 = nullptr, *dpp_b1 = nullptr, *dpp_g2 = nullptr, *dpp_b2 = nullptr;
+  int dp_cond_off = -1;
+  // flow
+  std::vector<CouplingW> couplings;  // application order (flows.6, .4, .2, .0)
+  int flow_hidden = 0, flow_layers = 0, flow_kernel = 5;
+  // decoder
+  Lin dec_pre;
+  int dec_cond_off = -1;
+  std::vector<UpW> ups;
+  std::vector<ResBlockW> rbs;
+  const float* post_w = nullptr;
+  int post_k = 7, post_c = 0;
+  // speaker conditioning: all cond layers as one GEMM (G -> n_cond)
+  const float* emb_g = nullptr;
+  Lin cond_all;
+  int n_cond = 0;
+
+  ~DeviceVoice();
+};
+
+std::unique_ptr<DeviceVoice> build_device_voice(const HostVoice& hv, int device);
+
+struct Arena {
+  char* base = nullptr;
+  size_t cap = 0, used = 0;
+  void reset() { used = 0; }
+  void reserve(size_t bytes);  // grows (cudaFree + cudaMalloc) if needed; contents lost
+  template <typename T>
+  T* alloc(size_t n) {
+    size_t bytes = (n * sizeof(T) + 255) & ~size_t(255);
+    if (used + bytes > cap) throw EngineError(4, "internal: workspace arena overflow");
+    T* p = reinterpret_cast<T*>(base + used);
+    used += bytes;
+    return p;
+  }
+  ~Arena();
+};
+
+struct PinnedBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  void reserve(size_t bytes);
+  ~PinnedBuf();
+};
+
+struct Context {  // per concurrent call: stream + workspaces (SURVEY.md §8b threading row)
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  Arena a1, a2;
+  PinnedBuf h_in, h_meta, h_pcm, h_audio;
+  explicit Context(int dev);
+  ~Context();
+};
+
+struct DebugTensor {
+  std::vector<float> data;
+  int64_t rows = 0, cols = 0;
+};
+
+struct Result {
+  int batch = 0;
+  std::vector<int64_t> sample_off, frames;
+  std::vector<float> peaks;
+  const int16_t* pcm = nullptr;   // pinned, owned by ctx
+  const float* audio = nullptr;   // pinned, owned by ctx
+  const void* d_pcm = nullptr;    // device, owned by ctx
+  double device_ms = 0;
+  int64_t launches = 0;
+  std::map<std::string, DebugTensor> debug;
+  struct Voice* owner = nullptr;
+  Context* ctx = nullptr;  // leased until the result is freed
+};
+
+struct Voice {
+  std::unique_ptr<DeviceVoice> dv;
+  std::mutex mu;
+  std::vector<Context*> idle;
+  std::vector<std::unique_ptr<Context>> all;
+  Context* acquire();
+  void release(Context* c);
+};
+
+Result* run_inference(Voice& v, const int64_t* ids, const int64_t* lengths, int batch, int t_stride,
+                      const float* scales, const int64_t* sid, uint64_t seed, uint32_t flags);
+
+}  // namespace m3

@@ -1,0 +1,92 @@
+// Kernel launch interface of the engine (host side).  All activations are fp32,
+// channels-last, utterances packed back to back: row r of utterance b at level L lives at
+// (seg_off[b] * scale_L + r).  No padded rows exist, so VITS' mask multiplications
+//  reduce to per-utterance zero padding at segment edges, which is
+// exactly the batch-1 behaviour of the reference (mimic3_tts/voice.py:180-181).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace m3 {
+
+extern thread_local int64_t g_launch_count;  // kernels launched by this thread's current call
+
+struct ConvParams {
+  // input
+  const float* in = nullptr;
+  int in_stride = 0, in_coff = 0, Cin = 0;
+  float in_slope = 1.f;  // leaky-relu applied to the input on load (1 = identity)
+  // weights [phase][tap][Cin][ldw], ldw = Cout (2*Cout when gate)
+  const float* W = nullptr;
+  long long w_phase_stride = 0;
+  int Cout = 0, taps = 1, dil = 1, pad_left = 0;
+  const float* bias = nullptr;   // [ldw]
+  const float* ubias = nullptr;  // per-utterance bias [B][ub_stride] (+ column offset folded in pointer)
+  int ub_stride = 0;
+  // epilogue: v = acc + bias + ubias; (gate) v = tanh(va)*sigmoid(vb); v += res; v *= scale; act; mode
+  int gate = 0;
+  const float* res = nullptr;
+  int res_stride = 0, res_coff = 0;
+  float scale = 1.f;
+  int act = 0;   // 0 none, 1 relu
+  int mode = 0;  // 0 store, 1 accumulate (out += v), 2 subtract (out -= v)
+  float* out = nullptr;
+  int out_stride = 0, out_coff = 0;
+  float* out2 = nullptr;  // columns >= split go to out2[col - split]
+  int out2_stride = 0, split = 1 << 30;
+  // segments
+  const int* seg_off = nullptr;
+  const int* seg_len = nullptr;
+  int in_scale = 1;    // input rows per segment unit
+  int out_scale = 1;   // output rows per segment unit
+  int rows_extra = 0;  // GEMM rows = len*in_scale + rows_extra
+  int out_mul = 1, out_add = 0, out_add_phase = 0;  // out row = t*out_mul + out_add + phase*out_add_phase
+  int phases = 1;
+};
+
+void launch_conv(const ConvParams& p, int n_seg, int max_seg_len, cudaStream_t st);
+
+// out = res + act(LN(a + b)) over channels, eps 1e-5; act: 0 none, 1 erf-GELU
+void launch_layernorm(const float* a, const float* b, const float* res, const float* gamma, const float* beta,
+                      float* out, int rows, int C, int act, cudaStream_t st);
+// y = GELU(LN(depthwise_conv_k3(x, dilation) + bias)) (DDSConv first half), segment aware
+void launch_dds_sep(const float* x, const float* w /*[3][C]*/, const float* bias, const float* gamma,
+                    const float* beta, float* out, int C, int dil, const int* seg_off, const int* seg_len, int n_seg,
+                    int max_len, cudaStream_t st);
+// out[t][c] = in[t][c] + ubias[seg][c]
+void launch_add_ubias(const float* in, const float* ubias, int ub_stride, float* out, int C, const int* seg_off,
+                      const int* seg_len, int n_seg, int max_len, cudaStream_t st);
+void launch_embedding(const int64_t* ids, int t_stride, const float* emb, int num_symbols, float scale, float* out, int H,
+                      const int* seg_off, const int* seg_len, int n_seg, int max_len, cudaStream_t st);
+void launch_gather_rows(const int64_t* idx, const float* table, float* out, int n, int C, cudaStream_t st);
+// relative-position multi-head self attention (window W), qkv [rows][3H]
+void launch_attention(const float* qkv, const float* emb_rel_k, const float* emb_rel_v, float* out, int H,
+                      int n_heads, int window, const int* seg_off, const int* seg_len, int n_seg, int max_len,
+                      cudaStream_t st);
+// u[t][c] = z[t][zc]*w[c] + b[c] + h[t][c]
+void launch_convflow_pre(const float* z, int zc, const float* w, const float* b, const float* h, float* out,
+                         int rows, int C, cudaStream_t st);
+// z[t][zc] = RQS^-1(z[t][zc] | params[t][0:29] scaled)
+void launch_rqs_inverse(float* z, int zc, const float* params, int pstride, float inv_sqrt_c, int rows,
+                        cudaStream_t st);
+void launch_sdp_noise(float* z, float noise_w, uint64_t seed, const int* seg_off, const int* seg_len, int n_seg,
+                      int max_len, cudaStream_t st);
+// logw = (z[:, zc] - m) * exp(-logs)
+void launch_sdp_finish(const float* z, int zc, float m, float logs, float* logw, int rows, cudaStream_t st);
+// durations: w_ceil = ceil(exp(logw)*length_scale); cum = inclusive scan per utterance; frames[b] = max(1, total)
+void launch_durations(const float* logw, int logw_stride, float length_scale, int* cum, int* frames,
+                      const int* seg_off, const int* seg_len, int n_seg, cudaStream_t st);
+// z_p[frame][c] = m[tok][c] + N(0,1)*exp(logs[tok][c])*noise_scale  (stats = [m | logs], stride 2I)
+void launch_expand(const float* stats, int I, const int* cum, const int* tok_off, const int* tok_len,
+                   const int* frm_off, const int* frm_len, int n_seg, int max_frames, float noise_scale,
+                   uint64_t seed, float* zp, cudaStream_t st);
+void launch_flip_channels(float* x, int rows, int C, cudaStream_t st);
+// y = tanh(conv_k(lrelu(x, slope)))  (C_out = 1, no bias) + per-utterance max|y|
+void launch_conv_post(const float* x, int C, const float* w /*[k][C]*/, int k, float slope, float* audio,
+                      unsigned* peak_bits, const int* seg_off, const int* seg_len, int scale, int n_seg, int max_len,
+                      cudaStream_t st);
+// pcm = trunc(clip(audio * 32767/max(0.01, peak)))  (mimic3_tts/utils.py:237-244)
+void launch_to_int16(const float* audio, const unsigned* peak_bits, int16_t* pcm, const int* seg_off,
+                     const int* seg_len, int scale, int n_seg, int max_len, cudaStream_t st);
+
+}  // namespace m3

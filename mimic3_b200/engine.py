@@ -1,0 +1,243 @@
+"""ctypes binding of ``libm3b200.so`` (C ABI in ``include/m3b200.h``).
+
+:class:`B200Session` duck-types the one method Mimic 3 calls on its
+``onnxruntime.InferenceSession`` -- ``run(None, inputs)`` at reference
+``mimic3_tts/voice.py:230`` -- so it can sit where ``onnx_model`` goes
+(``voice.py:77,83``).  There is **no CPU fallback**: if the CUDA library or an
+sm_100 GPU is missing, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+from pathlib import Path
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+M3_OK, M3_ERR_INVALID, M3_ERR_IO, M3_ERR_MODEL, M3_ERR_CUDA, M3_ERR_NOGPU = range(6)
+FLAG_KEEP_FLOAT, FLAG_DEBUG_TENSORS, FLAG_DEVICE_IDS, FLAG_NO_HOST_COPY = 1, 2, 4, 8
+
+_LIB_NAME = "libm3b200.so"
+_lib = None
+_lib_lock = threading.Lock()
+
+# Every symbol include/m3b200.h declares (tests check the .so exports all of them).
+API_SYMBOLS = [
+    "m3_version", "m3_last_error", "m3_device_count", "m3_voice_load", "m3_voice_free",
+    "m3_voice_get_info", "m3_infer", "m3_result_batch", "m3_result_sample_offsets",
+    "m3_result_num_frames", "m3_result_pcm", "m3_result_audio", "m3_result_peaks",
+    "m3_result_device_pcm", "m3_result_device_ms", "m3_result_kernel_launches",
+    "m3_result_tensor", "m3_result_free",
+]
+
+
+class B200EngineError(RuntimeError):
+    """libm3b200 reported a failure (model, I/O, CUDA, or no sm_100 GPU)."""
+
+
+class VoiceInfo(C.Structure):
+    _fields_ = [
+        ("num_symbols", C.c_int32), ("n_speakers", C.c_int32), ("is_multispeaker", C.c_int32),
+        ("has_speaker_embedding", C.c_int32), ("sample_rate", C.c_int32), ("hop_length", C.c_int32),
+        ("hidden_channels", C.c_int32), ("inter_channels", C.c_int32),
+        ("noise_scale", C.c_float), ("length_scale", C.c_float), ("noise_w", C.c_float),
+        ("n_params", C.c_int64), ("device", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+def library_path() -> Path:
+    env = os.environ.get("M3B200_LIBRARY")
+    return Path(env) if env else Path(__file__).resolve().parent / _LIB_NAME
+
+
+def load_library() -> C.CDLL:
+    """Load the CUDA library; raises (never falls back) if it is missing."""
+    global _lib
+    with _lib_lock:
+        if _lib is not None:
+            return _lib
+        path = library_path()
+        if not path.exists():
+            raise B200EngineError(
+                f"{path} not found: build it with `python -m mimic3_b200.build` "
+                "(the engine has no CPU fallback)")
+        lib = C.CDLL(str(path))
+        vp, i32, i64p = C.c_void_p, C.c_int32, C.POINTER(C.c_int64)
+        lib.m3_version.restype = C.c_char_p
+        lib.m3_last_error.restype = C.c_char_p
+        lib.m3_device_count.restype = i32
+        lib.m3_voice_load.restype = i32
+        lib.m3_voice_load.argtypes = [C.c_char_p, i32, C.POINTER(vp)]
+        lib.m3_voice_free.restype = None
+        lib.m3_voice_free.argtypes = [vp]
+        lib.m3_voice_get_info.restype = i32
+        lib.m3_voice_get_info.argtypes = [vp, C.POINTER(VoiceInfo)]
+        lib.m3_infer.restype = i32
+        lib.m3_infer.argtypes = [vp, vp, i64p, i32, i32, C.POINTER(C.c_float), i64p, C.c_uint64,
+                                 C.c_uint32, C.POINTER(vp)]
+        lib.m3_result_batch.restype = i32
+        lib.m3_result_batch.argtypes = [vp]
+        for name, rt in (("m3_result_sample_offsets", i64p), ("m3_result_num_frames", i64p),
+                         ("m3_result_pcm", C.POINTER(C.c_int16)), ("m3_result_audio", C.POINTER(C.c_float)),
+                         ("m3_result_peaks", C.POINTER(C.c_float)), ("m3_result_device_pcm", vp)):
+            getattr(lib, name).restype = rt
+            getattr(lib, name).argtypes = [vp]
+        lib.m3_result_device_ms.restype = C.c_double
+        lib.m3_result_device_ms.argtypes = [vp]
+        lib.m3_result_kernel_launches.restype = C.c_int64
+        lib.m3_result_kernel_launches.argtypes = [vp]
+        lib.m3_result_tensor.restype = i32
+        lib.m3_result_tensor.argtypes = [vp, C.c_char_p, C.POINTER(C.POINTER(C.c_float)), i64p, i64p]
+        lib.m3_result_free.restype = None
+        lib.m3_result_free.argtypes = [vp]
+        _lib = lib
+        return lib
+
+
+def _raise(lib, code: int):
+    msg = lib.m3_last_error().decode("utf-8", "replace")
+    if code == M3_ERR_INVALID:
+        raise ValueError(msg)
+    if code == M3_ERR_IO:
+        raise FileNotFoundError(msg)
+    raise B200EngineError(f"[m3b200 error {code}] {msg}")
+
+
+class InferenceResult:
+    """Outputs of one engine call (all arrays are owned copies)."""
+
+    __slots__ = ("pcm", "audio", "sample_offsets", "frames", "peaks", "device_ms", "launches",
+                 "tensors", "device_pcm_ptr")
+
+    def utterance_pcm(self, b: int) -> np.ndarray:
+        return self.pcm[self.sample_offsets[b]:self.sample_offsets[b + 1]]
+
+    def utterance_audio(self, b: int) -> np.ndarray:
+        return self.audio[self.sample_offsets[b]:self.sample_offsets[b + 1]]
+
+    @property
+    def total_samples(self) -> int:
+        return int(self.sample_offsets[-1])
+
+
+class B200Session:
+    """Stands where ``onnxruntime.InferenceSession(generator.onnx)`` stands in Mimic 3."""
+
+    def __init__(self, path, sess_options=None, providers=None, device: Optional[int] = None):
+        self._lib = load_library()
+        if device is None:
+            device = int(os.environ.get("M3B200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+        handle = C.c_void_p()
+        rc = self._lib.m3_voice_load(str(path).encode(), int(device), C.byref(handle))
+        if rc != M3_OK:
+            _raise(self._lib, rc)
+        self._h = handle
+        info = VoiceInfo()
+        self._lib.m3_voice_get_info(self._h, C.byref(info))
+        self.info = info
+        self.device = int(info.device)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.m3_voice_free(self._h)
+            self._h = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- engine-native call ----------------------------------------------------------
+    def infer(self, ids: np.ndarray, lengths: np.ndarray, scales: Sequence[float],
+              sid: Optional[np.ndarray] = None, seed: int = 0, keep_float: bool = False,
+              debug_tensors: Sequence[str] = (), host_copy: bool = True,
+              device_ids_ptr: Optional[int] = None) -> InferenceResult:
+        lengths = np.ascontiguousarray(lengths, dtype=np.int64)
+        batch = int(lengths.shape[0])
+        flags = 0
+        if device_ids_ptr is not None:
+            ids_ptr = C.c_void_p(int(device_ids_ptr))
+            t_stride = int(ids)  # caller passes the row stride in `ids`
+            flags |= FLAG_DEVICE_IDS
+        else:
+            ids = np.ascontiguousarray(ids, dtype=np.int64)
+            if ids.ndim != 2 or ids.shape[0] != batch:
+                raise ValueError("ids must be int64 (batch, T) matching input_lengths")
+            t_stride = int(ids.shape[1])
+            ids_ptr = ids.ctypes.data_as(C.c_void_p)
+        sc = (C.c_float * 3)(*[float(s) for s in scales])
+        sid_p = None
+        if sid is not None:
+            sid = np.ascontiguousarray(sid, dtype=np.int64)
+            if sid.shape != (batch,):
+                raise ValueError("sid must have shape (batch,)")
+            sid_p = sid.ctypes.data_as(C.POINTER(C.c_int64))
+        if keep_float:
+            flags |= FLAG_KEEP_FLOAT
+        if debug_tensors:
+            flags |= FLAG_DEBUG_TENSORS
+        if not host_copy:
+            flags |= FLAG_NO_HOST_COPY
+        res = C.c_void_p()
+        rc = self._lib.m3_infer(self._h, ids_ptr, lengths.ctypes.data_as(C.POINTER(C.c_int64)), batch,
+                                t_stride, sc, sid_p, C.c_uint64(seed & (2 ** 64 - 1)), flags, C.byref(res))
+        if rc != M3_OK:
+            _raise(self._lib, rc)
+        try:
+            out = InferenceResult()
+            off = np.ctypeslib.as_array(self._lib.m3_result_sample_offsets(res), (batch + 1,)).copy()
+            out.sample_offsets = off
+            out.frames = np.ctypeslib.as_array(self._lib.m3_result_num_frames(res), (batch,)).copy()
+            out.peaks = np.ctypeslib.as_array(self._lib.m3_result_peaks(res), (batch,)).copy()
+            total = int(off[-1])
+            out.pcm = out.audio = None
+            if host_copy:
+                out.pcm = np.ctypeslib.as_array(self._lib.m3_result_pcm(res), (max(total, 1),))[:total].copy()
+                if keep_float:
+                    out.audio = np.ctypeslib.as_array(self._lib.m3_result_audio(res), (max(total, 1),))[:total].copy()
+            out.device_ms = float(self._lib.m3_result_device_ms(res))
+            out.launches = int(self._lib.m3_result_kernel_launches(res))
+            out.device_pcm_ptr = self._lib.m3_result_device_pcm(res)
+            out.tensors = {}
+            for name in debug_tensors:
+                data = C.POINTER(C.c_float)()
+                rows, cols = C.c_int64(), C.c_int64()
+                rc = self._lib.m3_result_tensor(res, name.encode(), C.byref(data), C.byref(rows), C.byref(cols))
+                if rc == M3_OK:
+                    n = rows.value * cols.value
+                    out.tensors[name] = np.ctypeslib.as_array(data, (max(n, 1),))[:n].copy().reshape(rows.value, cols.value)
+            return out
+        finally:
+            self._lib.m3_result_free(res)
+
+    # -- onnxruntime-compatible call (voice.py:230) ---------------------------------------
+    def run(self, output_names, input_feed: Dict[str, np.ndarray], run_options=None) -> List[np.ndarray]:
+        """``[float32 (B, 1, S_max)]`` like the exported graph's "output" (zero padded)."""
+        for key in input_feed:
+            if key not in ("input", "input_lengths", "scales", "sid"):
+                raise ValueError(f"Invalid input name: {key}")
+        for key in ("input", "input_lengths", "scales"):
+            if key not in input_feed:
+                raise ValueError(f"Missing input: {key}")
+        if self.info.has_speaker_embedding and "sid" not in input_feed:
+            raise ValueError("Missing input: sid")
+        scales = np.asarray(input_feed["scales"], dtype=np.float32).reshape(-1)
+        if scales.shape[0] != 3:
+            raise ValueError("scales must have 3 elements [noise_scale, length_scale, noise_w]")
+        sid = input_feed.get("sid") if self.info.has_speaker_embedding else None
+        r = self.infer(np.asarray(input_feed["input"]), np.asarray(input_feed["input_lengths"]).reshape(-1),
+                       scales, None if sid is None else np.asarray(sid).reshape(-1), keep_float=True,
+                       seed=int.from_bytes(os.urandom(8), "little") if (scales[0] or scales[2]) else 0)
+        batch = len(r.frames)
+        smax = int(np.max(np.diff(r.sample_offsets)))
+        out = np.zeros((batch, 1, smax), dtype=np.float32)
+        for b in range(batch):
+            a = r.utterance_audio(b)
+            out[b, 0, : a.shape[0]] = a
+        return [out]
+
+    def get_providers(self):
+        return ["B200ExecutionProvider"]

@@ -1,0 +1,216 @@
+"""Host-side mirror of ``Mimic3Voice`` for the ids->audio hot path.
+
+Same names, argument meaning and error behaviour as the reference
+(``mimic3_tts/voice.py``): :meth:`B200Voice.ids_to_audio` follows ``voice.py:154-243``
+line by line, :meth:`B200Voice.load_from_directory` reads the same voice directory
+(``voice.py:246-321``), and sessions are shared per ``generator.onnx`` path under a
+lock (``voice.py:71-72,277-299``).  The text front-ends (``text_to_phonemes`` --
+gruut / espeak-ng / epitran, ``voice.py:413-775``) are out of scope:
+ids are the engine's input.  The one addition is :meth:`ids_to_audio_batch`.
+"""
+from __future__ import annotations
+
+import csv
+import json
+import logging
+import threading
+import time
+import typing
+from pathlib import Path
+from types import SimpleNamespace
+
+import numpy as np
+
+from .engine import B200Session
+
+_LOGGER = logging.getLogger(__name__)
+
+DEFAULT_RATE = 1.0
+B200_PROVIDER = "B200ExecutionProvider"
+
+
+def _ns(d):
+    if isinstance(d, dict):
+        return SimpleNamespace(**{k: _ns(v) for k, v in d.items()})
+    if isinstance(d, list):
+        return [_ns(v) for v in d]
+    return d
+
+
+class VoiceConfig:
+    """The parts of ``TrainingConfig`` (``mimic3_tts/config.py:274-327``) the path reads."""
+
+    def __init__(self, data: dict):
+        self.raw = data
+        audio = {"sample_rate": 22050, "hop_length": 256, **data.get("audio", {})}
+        inference = {"length_scale": 1.0, "noise_scale": 0.667, "noise_w": 0.8, **data.get("inference", {})}
+        model = {"n_speakers": 1, **data.get("model", {})}
+        self.audio = _ns(audio)
+        self.inference = _ns(inference)
+        self.model = _ns(model)
+        self.datasets = [_ns(d) for d in data.get("datasets", [])]
+        self.phonemizer = data.get("phonemizer")
+        self.text_language = data.get("text_language")
+
+    @property
+    def is_multispeaker(self) -> bool:  # config.py:316-318
+        return self.model.n_speakers > 1 or any(getattr(d, "multispeaker", False) for d in self.datasets)
+
+    @staticmethod
+    def load(config_file: typing.TextIO) -> "VoiceConfig":
+        return VoiceConfig(json.loads(config_file.read()))
+
+
+def load_phoneme_ids(ids_file: typing.TextIO) -> typing.Dict[str, int]:
+    """``phonemes.txt``: one ``<id> <phoneme>`` per line (what ``phonemes2ids.load_phoneme_ids``
+    reads at ``voice.py:268-271``)."""
+    out: typing.Dict[str, int] = {}
+    for line in ids_file:
+        line = line.rstrip("\n")
+        if not line.strip() or line.startswith("#"):
+            continue
+        pid, _, phoneme = line.partition(" ")
+        out[phoneme] = int(pid)
+    return out
+
+
+class B200Voice:
+    """Drop-in for the ids->audio half of ``Mimic3Voice`` backed by libm3b200."""
+
+    _SHARED_MODELS: typing.Dict[str, B200Session] = {}
+    _SHARED_MODELS_LOCK = threading.Lock()
+
+    def __init__(self, config, onnx_model, phoneme_to_id, phoneme_map=None, speaker_map=None):
+        self.config = config
+        self.onnx_model = onnx_model
+        self.phoneme_to_id = phoneme_to_id
+        self.phoneme_map = phoneme_map
+        self.speaker_map = speaker_map
+
+    # -- voice.py:89 ------------------------------------------------------------------
+    def text_to_phonemes(self, text, text_language=None):
+        raise NotImplementedError(
+            "text front-ends are outside the B200 hot path; use the reference Mimic3Voice "
+            "subclasses and pass their ids to ids_to_audio (see INTEGRATION.md)")
+
+    def _resolve_speaker(self, speaker) -> int:
+        """voice.py:196-215."""
+        speaker_id = 0
+        if isinstance(speaker, str):
+            if self.speaker_map:
+                maybe = self.speaker_map.get(speaker)
+                if maybe is None:
+                    try:
+                        speaker_id = int(speaker)
+                    except ValueError:
+                        _LOGGER.warning(
+                            "Unable to find a speaker with the name '%s'. Falling back to first speaker.", speaker)
+                else:
+                    speaker_id = maybe
+            # (reference: a str speaker without a speaker_map is ignored -> id 0)
+        elif speaker is not None:
+            speaker_id = speaker
+        return int(speaker_id)
+
+    def _scales(self, length_scale, noise_scale, noise_w, rate):
+        """voice.py:166-178."""
+        if length_scale is None:
+            length_scale = self.config.inference.length_scale
+        if rate > 0:
+            length_scale /= rate
+        if noise_scale is None:
+            noise_scale = self.config.inference.noise_scale
+        if noise_w is None:
+            noise_w = self.config.inference.noise_w
+        return np.array([noise_scale, length_scale, noise_w], dtype=np.float32)
+
+    # -- voice.py:154-243 -------------------------------------------------------------------
+    def ids_to_audio(self, phoneme_ids, speaker=None, length_scale=None, noise_scale=None, noise_w=None,
+                     rate: float = DEFAULT_RATE, seed: typing.Optional[int] = None) -> np.ndarray:
+        """Synthesize int16 audio from phoneme ids (one utterance)."""
+        return self.ids_to_audio_batch([phoneme_ids], [speaker], length_scale, noise_scale, noise_w, rate, seed)[0]
+
+    def ids_to_audio_batch(self, batch_ids, speakers=None, length_scale=None, noise_scale=None, noise_w=None,
+                           rate: float = DEFAULT_RATE, seed: typing.Optional[int] = None,
+                           ) -> typing.List[np.ndarray]:
+        """Batched extension: every utterance keeps batch-1 edge semantics
+        and its own peak normalisation, so ``out[i]`` equals ``ids_to_audio(batch_ids[i])``."""
+        scales = self._scales(length_scale, noise_scale, noise_w, rate)
+        n = len(batch_ids)
+        lengths = np.array([len(p) for p in batch_ids], dtype=np.int64)
+        text = np.zeros((n, max(1, int(lengths.max()) if n else 1)), dtype=np.int64)
+        for i, p in enumerate(batch_ids):
+            text[i, : len(p)] = np.asarray(p, dtype=np.int64)
+        sid = None
+        if self.config.is_multispeaker:
+            speakers = speakers if speakers is not None else [None] * n
+            sid = np.array([self._resolve_speaker(s) for s in speakers], dtype=np.int64)
+        _LOGGER.debug("TTS settings: speaker-id=%s, length-scale=%s, noise-scale=%s, noise-w=%s",
+                      None if sid is None else sid.tolist(), scales[1], scales[0], scales[2])
+        start_time = time.perf_counter()
+        if seed is None:
+            seed = int(np.random.randint(0, 2 ** 31 - 1)) if (scales[0] or scales[2]) else 0
+        if sid is not None and not self.onnx_model.info.has_speaker_embedding:
+            sid = None  # config says multispeaker but the graph has no "sid" input
+        r = self.onnx_model.infer(text, lengths, scales, sid, seed=seed)
+        audios = [r.utterance_pcm(b) for b in range(n)]
+        end_time = time.perf_counter()
+        audio_sec = r.total_samples / self.config.audio.sample_rate
+        _LOGGER.debug("RTF: %s", (end_time - start_time) / audio_sec if audio_sec > 0 else 0.0)
+        return audios
+
+    # -- voice.py:245-376 ------------------------------------------------------------------------
+    @staticmethod
+    def load_from_directory(voice_dir, session_options=None, providers=None, share_models: bool = True,
+                            use_deterministic_compute: bool = False, device: typing.Optional[int] = None,
+                            ) -> "B200Voice":
+        voice_dir = Path(voice_dir)
+        _LOGGER.debug("Loading voice from %s", voice_dir)
+        with open(voice_dir / "config.json", "r", encoding="utf-8") as config_file:
+            config = VoiceConfig.load(config_file)
+        with open(voice_dir / "phonemes.txt", "r", encoding="utf-8") as ids_file:
+            phoneme_to_id = load_phoneme_ids(ids_file)
+        generator_path = voice_dir / "generator.onnx"
+        if share_models:
+            with B200Voice._SHARED_MODELS_LOCK:
+                model_key = f"{generator_path.absolute()}@{device}"
+                onnx_model = B200Voice._SHARED_MODELS.get(model_key)
+                if onnx_model is None:
+                    onnx_model = B200Voice._load_model(generator_path, session_options, providers,
+                                                       use_deterministic_compute, device)
+                    B200Voice._SHARED_MODELS[model_key] = onnx_model
+                else:
+                    _LOGGER.debug("Using shared B200 model (%s)", model_key)
+        else:
+            onnx_model = B200Voice._load_model(generator_path, session_options, providers,
+                                               use_deterministic_compute, device)
+        phoneme_map = None
+        phoneme_map_path = voice_dir / "phoneme_map.txt"
+        if phoneme_map_path.is_file():
+            phoneme_map = {}
+            with open(phoneme_map_path, "r", encoding="utf-8") as map_file:
+                for line in map_file:
+                    parts = line.strip("\r\n").split(" ")
+                    if len(parts) >= 2 and parts[0]:
+                        phoneme_map[parts[0]] = parts[1:]
+        speaker_map = None
+        speaker_map_path = voice_dir / "speaker_map.csv"
+        if speaker_map_path.is_file():
+            with open(speaker_map_path, "r", encoding="utf-8") as map_file:
+                reader = csv.reader(map_file, delimiter="|")
+                speaker_map = {}
+                for row in reader:
+                    if not row:
+                        continue
+                    speaker_id = int(row[0])
+                    for alias in row[2:]:
+                        speaker_map[alias] = speaker_id
+        return B200Voice(config=config, onnx_model=onnx_model, phoneme_to_id=phoneme_to_id,
+                         phoneme_map=phoneme_map, speaker_map=speaker_map)
+
+    # -- voice.py:378-407 ------------------------------------------------------------------------
+    @staticmethod
+    def _load_model(generator_path, session_options=None, providers=None,
+                    use_deterministic_compute: bool = False, device: typing.Optional[int] = None) -> B200Session:
+        _LOGGER.debug("Loading model from %s", generator_path)
+        return B200Session(str(generator_path), sess_options=session_options, providers=providers, device=device)

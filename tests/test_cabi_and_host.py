@@ -1,0 +1,126 @@
+"""CPU tests: the C-ABI library loads and exports every declared symbol; host-side mirror of
+Mimic3Voice behaves like the reference (mimic3_tts/voice.py:154-243); loader error paths."""
+import re
+import ctypes
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from mimic3_b200 import engine
+from mimic3_b200.voice import B200Voice, VoiceConfig, load_phoneme_ids
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_library_exports_every_declared_symbol(built_library):
+    header = (ROOT / "include" / "m3b200.h").read_text()
+    declared = sorted(set(re.findall(r"\b(m3_[a-z0-9_]+)\s*\(", header)))
+    assert declared == sorted(engine.API_SYMBOLS)
+    lib = ctypes.CDLL(str(built_library))
+    for name in declared:
+        assert hasattr(lib, name), name
+    lib.m3_version.restype = ctypes.c_char_p
+    assert b"sm_100a" in lib.m3_version()
+
+
+def test_library_is_sm100a_only(built_library):
+    import subprocess
+    out = subprocess.run(["cuobjdump", "-lelf", str(built_library)], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+def test_loader_errors_without_gpu_are_specific(built_library, voices, tmp_path):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only check")
+    lib = engine.load_library()
+    with pytest.raises(engine.B200EngineError, match="no CUDA device|no CPU fallback"):
+        engine.B200Session(str(voices("tiny_ms_folded")))  # parsed + bound fine, then: no GPU
+    with pytest.raises(FileNotFoundError):
+        engine.B200Session(str(tmp_path / "nope"))
+    # a voice whose generator.onnx lacks a tensor -> model error naming the tensor
+    from mimic3_b200 import synth_voice as sv
+    cfg = sv.tiny_config()
+    params = sv.make_params(cfg, 1)
+    sv.write_voice(tmp_path / "bad", cfg, seed=1)
+    del params["dec.conv_post.weight"]
+    sv.write_generator_onnx(tmp_path / "bad" / "generator.onnx", cfg, params)
+    with pytest.raises(engine.B200EngineError, match="dec.conv_post.weight"):
+        engine.B200Session(str(tmp_path / "bad"))
+    # shape mismatch between config.json and the graph
+    params = sv.make_params(cfg, 1)
+    params["enc_p.proj.weight"] = params["enc_p.proj.weight"][:-2]
+    sv.write_generator_onnx(tmp_path / "bad" / "generator.onnx", cfg, params)
+    with pytest.raises(engine.B200EngineError, match="enc_p.proj.weight"):
+        engine.B200Session(str(tmp_path / "bad"))
+    (tmp_path / "bad" / "generator.onnx").write_bytes(b"\x08\x07garbage")
+    with pytest.raises(engine.B200EngineError):
+        engine.B200Session(str(tmp_path / "bad"))
+
+
+class FakeSession:
+    """Records what the host layer sends to the engine."""
+
+    class info:
+        has_speaker_embedding = 1
+
+    def __init__(self):
+        self.calls = []
+
+    def infer(self, text, lengths, scales, sid, seed=0, **kw):
+        self.calls.append(dict(text=text.copy(), lengths=lengths.copy(), scales=scales.copy(),
+                               sid=None if sid is None else sid.copy(), seed=seed))
+
+        class R:
+            total_samples = int(lengths.sum()) * 4
+            def utterance_pcm(self_, b):
+                return np.zeros(int(lengths[b]) * 4, dtype=np.int16)
+        return R()
+
+
+def _voice(multispeaker=True, speaker_map=None):
+    cfg = VoiceConfig({"model": {"n_speakers": 3 if multispeaker else 1},
+                       "inference": {"length_scale": 1.2, "noise_scale": 0.5, "noise_w": 0.7}})
+    return B200Voice(cfg, FakeSession(), {}, None, speaker_map)
+
+
+def test_ids_to_audio_builds_reference_inputs():
+    v = _voice(speaker_map={"p239": 2, "alias": 1})
+    v.ids_to_audio([3, 4, 5, 6], speaker="p239", rate=2.0)
+    c = v.onnx_model.calls[-1]
+    assert c["text"].dtype == np.int64 and c["text"].shape == (1, 4)          # voice.py:180
+    assert c["lengths"].tolist() == [4]                                        # voice.py:181
+    np.testing.assert_allclose(c["scales"], [0.5, 0.6, 0.7])                   # [noise, length/rate, noise_w] :182-189, :170
+    assert c["scales"].dtype == np.float32 and c["sid"].tolist() == [2]
+    v.ids_to_audio([3], speaker="1")               # not in map -> int()  (voice.py:203-205)
+    assert v.onnx_model.calls[-1]["sid"].tolist() == [1]
+    v.ids_to_audio([3], speaker="nobody")          # warning + first speaker (voice.py:206-211)
+    assert v.onnx_model.calls[-1]["sid"].tolist() == [0]
+    v.ids_to_audio([3], speaker=2, length_scale=0.9, noise_scale=0.0, noise_w=0.0, rate=0)
+    c = v.onnx_model.calls[-1]
+    np.testing.assert_allclose(c["scales"], [0.0, 0.9, 0.0])                   # rate <= 0: no scaling (voice.py:170)
+    assert c["sid"].tolist() == [2] and c["seed"] == 0
+    single = _voice(multispeaker=False)
+    single.ids_to_audio([1, 2], speaker="p239")
+    assert single.onnx_model.calls[-1]["sid"] is None                          # no "sid" key (voice.py:197)
+
+
+def test_batch_padding_and_lengths():
+    v = _voice(speaker_map={"a": 1})
+    out = v.ids_to_audio_batch([[1, 2, 3], [4], [5, 6]], speakers=["a", None, 2], noise_scale=0, noise_w=0)
+    c = v.onnx_model.calls[-1]
+    assert c["text"].shape == (3, 3) and c["lengths"].tolist() == [3, 1, 2]
+    assert c["text"][1].tolist() == [4, 0, 0] and c["sid"].tolist() == [1, 0, 2]
+    assert [len(o) for o in out] == [12, 4, 8]
+
+
+def test_voice_directory_files(voices):
+    d = voices("tiny_ms")
+    with open(d / "phonemes.txt", encoding="utf-8") as f:
+        p2i = load_phoneme_ids(f)
+    assert p2i["_"] == 0 and len(p2i) == 20
+    cfg = VoiceConfig.load(open(d / "config.json"))
+    assert cfg.is_multispeaker and cfg.audio.sample_rate == 22050
+    assert cfg.inference.noise_w == pytest.approx(0.8)

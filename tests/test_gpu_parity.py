@@ -1,0 +1,208 @@
+"""GPU parity tests: the CUDA engine (through the C ABI) against the CPU oracle.
+
+Bar (BASELINE.json north_star): identical integer durations, waveform RMS error <= 1e-3
+per utterance against the fp32 reference restatement; int16 PCM within 1 LSB wherever
+the float waveform matches to fp32 accuracy.
+"""
+import numpy as np
+import pytest
+
+from conftest import rand_ids
+
+pytestmark = pytest.mark.gpu
+
+RMS_TOL = 1e-3  # north_star: "waveform RMS error vs fp32 reference <= 1e-3"
+
+
+@pytest.fixture(scope="module")
+def sessions(built_library, voices):
+    from mimic3_b200.engine import B200Session
+    cache = {}
+
+    def get(name):
+        if name not in cache:
+            cache[name] = B200Session(str(voices(name)))
+        return cache[name]
+    yield get
+    for s in cache.values():
+        s.close()
+
+
+@pytest.fixture(scope="module")
+def oracles(voices):
+    from oracle.vits_oracle import VitsOracle
+    cache = {}
+
+    def get(name):
+        if name not in cache:
+            cache[name] = VitsOracle(str(voices(name)))
+        return cache[name]
+    return get
+
+
+def _batch(rng, nsym, lengths):
+    T = max(lengths)
+    ids = np.zeros((len(lengths), T), dtype=np.int64)
+    for b, L in enumerate(lengths):
+        ids[b, :L] = rand_ids(rng, nsym, L)
+    return ids, np.array(lengths, dtype=np.int64)
+
+
+def _compare(sess, orc, ids, lengths, scales, sid=None, seed=0, tol=RMS_TOL):
+    from oracle.vits_oracle import audio_float_to_int16
+    r = sess.infer(ids, lengths, scales, sid, seed=seed, keep_float=True,
+                   debug_tensors=("durations", "x", "stats", "logw", "z_p", "z"))
+    worst = 0.0
+    tok = 0
+    for b, L in enumerate(lengths):
+        audio, inter = orc.infer(ids[b, :L], scales, sid=None if sid is None else int(sid[b]), seed=seed, row=b,
+                                 return_intermediates=True)
+        dur = r.tensors["durations"][tok:tok + L, 0].astype(np.int64)
+        np.testing.assert_array_equal(dur, inter["durations"], err_msg=f"durations differ (utt {b})")
+        assert r.frames[b] == max(1, int(inter["durations"].sum()))
+        got = r.utterance_audio(b)
+        assert got.shape == audio.shape
+        rms = float(np.sqrt(np.mean((got - audio) ** 2)))
+        worst = max(worst, rms)
+        assert rms <= tol, f"utt {b}: waveform RMS {rms:.3e} > {tol}"
+        np.testing.assert_allclose(r.tensors["x"][tok:tok + L], inter["x"], atol=2e-4, rtol=1e-4)
+        np.testing.assert_allclose(r.tensors["logw"][tok:tok + L, 0], inter["logw"], atol=2e-4, rtol=1e-4)
+        # the engine's own int16 conversion is bit-exact w.r.t. the reference formula on ITS float audio
+        np.testing.assert_array_equal(r.utterance_pcm(b), audio_float_to_int16(got))
+        assert abs(float(r.peaks[b]) - float(np.abs(got).max())) == 0.0
+        tok += L
+    return worst
+
+
+@pytest.mark.parametrize("voice,multi", [("tiny", False), ("tiny_ms", True), ("tiny_rb1_dp", True)])
+def test_tiny_voices_deterministic_parity(sessions, oracles, voice, multi):
+    rng = np.random.default_rng(7)
+    sess, orc = sessions(voice), oracles(voice)
+    lengths = [17, 1, 40, 5, 9]
+    ids, lens = _batch(rng, sess.info.num_symbols, lengths)
+    sid = np.array([b % sess.info.n_speakers for b in range(len(lengths))]) if multi else None
+    worst = _compare(sess, orc, ids, lens, (0.0, 1.0, 0.0), sid)
+    print(f"{voice}: worst RMS {worst:.3e}")
+    worst = _compare(sess, orc, ids, lens, (0.0, 1.3, 0.0), sid)
+
+
+def test_export_styles_give_identical_audio(sessions):
+    rng = np.random.default_rng(3)
+    ids, lens = _batch(rng, 20, [12, 30])
+    sid = np.array([1, 2])
+    outs = [sessions(v).infer(ids, lens, (0.0, 1.0, 0.0), sid, keep_float=True) for v in
+            ("tiny_ms", "tiny_ms_folded", "tiny_ms_wn")]
+    np.testing.assert_array_equal(outs[0].audio, outs[1].audio)
+    assert outs[0].audio.shape == outs[2].audio.shape
+    assert np.sqrt(np.mean((outs[0].audio - outs[2].audio) ** 2)) < 1e-5
+
+
+def test_noise_on_parity_with_shared_philox(sessions, oracles):
+    """Noise > 0: reference RNG is irreproducible; engine and oracle share the Philox spec."""
+    rng = np.random.default_rng(9)
+    sess, orc = sessions("tiny_ms"), oracles("tiny_ms")
+    ids, lens = _batch(rng, 20, [21, 8, 33])
+    _compare(sess, orc, ids, lens, (0.667, 1.0, 0.8), np.array([0, 1, 2]), seed=1234)
+    a = sess.infer(ids, lens, (0.667, 1.0, 0.8), np.array([0, 1, 2]), seed=1).pcm
+    b = sess.infer(ids, lens, (0.667, 1.0, 0.8), np.array([0, 1, 2]), seed=2).pcm
+    assert a.shape != b.shape or not np.array_equal(a, b)
+
+
+def test_low_voice_parity_single_and_multispeaker(sessions, oracles):
+    rng = np.random.default_rng(11)
+    for voice, multi in (("low", False), ("low_ms", True)):
+        sess, orc = sessions(voice), oracles(voice)
+        ids, lens = _batch(rng, sess.info.num_symbols, [60, 23])
+        sid = np.array([0, 57]) if multi else None
+        worst = _compare(sess, orc, ids, lens, (0.0, 1.0, 0.0), sid)
+        print(f"{voice}: worst RMS {worst:.3e}")
+
+
+def test_batch_rows_equal_single_runs(sessions):
+    """Batch-1 edge semantics inside a ragged batch (SURVEY.md §7 hard part 3)."""
+    rng = np.random.default_rng(5)
+    sess = sessions("tiny_ms")
+    lengths = [9, 31, 2, 17]
+    ids, lens = _batch(rng, 20, lengths)
+    sid = np.array([2, 0, 1, 1])
+    r = sess.infer(ids, lens, (0.0, 1.0, 0.0), sid, keep_float=True)
+    for b, L in enumerate(lengths):
+        one = sess.infer(ids[b:b + 1, :L], lens[b:b + 1], (0.0, 1.0, 0.0), sid[b:b + 1], keep_float=True)
+        np.testing.assert_array_equal(one.audio, r.utterance_audio(b))
+        np.testing.assert_array_equal(one.pcm, r.utterance_pcm(b))
+
+
+def test_ort_style_run_and_errors(sessions):
+    sess = sessions("tiny_ms")
+    feed = {"input": np.array([[4, 5, 6, 7]], dtype=np.int64), "input_lengths": np.array([4], dtype=np.int64),
+            "scales": np.array([0.0, 1.0, 0.0], dtype=np.float32), "sid": np.array([1], dtype=np.int64)}
+    out = sess.run(None, feed)
+    assert len(out) == 1 and out[0].dtype == np.float32 and out[0].ndim == 3 and out[0].shape[:2] == (1, 1)
+    audio = out[0].squeeze()                       # voice.py:230
+    assert audio.size % sess.info.hop_length == 0 and np.abs(audio).max() <= 1.0
+    bad = dict(feed, input=np.array([[4, 99, 6, 7]], dtype=np.int64))
+    with pytest.raises(ValueError, match="outside"):
+        sess.run(None, bad)
+    with pytest.raises(ValueError, match="sid"):
+        sess.run(None, dict(feed, sid=np.array([3], dtype=np.int64)))
+    with pytest.raises(ValueError):
+        sess.run(None, {k: v for k, v in feed.items() if k != "sid"})
+    with pytest.raises(ValueError):
+        sess.run(None, dict(feed, input_lengths=np.array([0], dtype=np.int64)))
+    with pytest.raises(ValueError):
+        sess.run(None, dict(feed, input_lengths=np.array([5], dtype=np.int64)))
+    ok = sess.run(None, feed)                     # the engine survives bad calls
+    np.testing.assert_array_equal(ok[0], out[0])
+
+
+def test_thread_safety_shared_voice(sessions):
+    """One voice shared by worker threads, like the shared ORT session (voice.py:277-292)."""
+    import threading
+    sess = sessions("tiny_ms")
+    rng = np.random.default_rng(2)
+    jobs = [_batch(rng, 20, [int(rng.integers(3, 40)) for _ in range(3)]) for _ in range(8)]
+    want = [sess.infer(i, l, (0.0, 1.0, 0.0), np.zeros(3, dtype=np.int64)).pcm for i, l in jobs]
+    got = [None] * len(jobs)
+
+    def work(k):
+        for _ in range(3):
+            got[k] = sess.infer(jobs[k][0], jobs[k][1], (0.0, 1.0, 0.0), np.zeros(3, dtype=np.int64)).pcm
+    ts = [threading.Thread(target=work, args=(k,)) for k in range(len(jobs))]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    for w, g in zip(want, got):
+        np.testing.assert_array_equal(w, g)
+
+
+def test_full_size_properties_cfg2(sessions):
+    """BASELINE cfg2 shape (vctk_low-like, B=32, 100 ids, sid 0): size-independent properties."""
+    sess = sessions("low_ms")
+    rng = np.random.Generator(np.random.PCG64(1234))
+    ids = rng.integers(4, sess.info.num_symbols, size=(32, 100)).astype(np.int64)
+    lens = np.full(32, 100, dtype=np.int64)
+    sid = np.zeros(32, dtype=np.int64)
+    r = sess.infer(ids, lens, (0.0, 1.0, 0.0), sid, keep_float=True)
+    hop = sess.info.hop_length
+    assert np.all(np.diff(r.sample_offsets) == r.frames * hop)
+    for b in range(32):
+        pcm = r.utterance_pcm(b)
+        assert int(np.abs(pcm.astype(np.int32)).max()) == 32767       # like the reference goldens
+        assert np.isfinite(r.utterance_audio(b)).all() and np.abs(r.utterance_audio(b)).max() <= 1.0
+    r2 = sess.infer(ids, lens, (0.0, 1.0, 0.0), sid)
+    np.testing.assert_array_equal(r.pcm, r2.pcm)                       # idempotent / deterministic
+    sub = sess.infer(ids[5:7], lens[5:7], (0.0, 1.0, 0.0), sid[5:7])
+    np.testing.assert_array_equal(sub.pcm, r.pcm[r.sample_offsets[5]:r.sample_offsets[7]])
+    half = sess.infer(ids, lens, (0.0, 0.5, 0.0), sid)
+    assert half.total_samples < r.total_samples                        # length_scale monotone
+    assert r.launches > 0
+
+
+def test_b200voice_end_to_end(voices, built_library):
+    from mimic3_b200.voice import B200Voice
+    v = B200Voice.load_from_directory(voices("tiny_ms"))
+    v2 = B200Voice.load_from_directory(voices("tiny_ms"))
+    assert v.onnx_model is v2.onnx_model                                # shared per generator.onnx
+    a = v.ids_to_audio([4, 5, 6, 7, 8], speaker="p201", noise_scale=0.0, noise_w=0.0)
+    b = v.ids_to_audio_batch([[4, 5, 6, 7, 8], [9, 10]], speakers=["p201", "p200"], noise_scale=0.0, noise_w=0.0)
+    assert a.dtype == np.int16 and np.array_equal(a, b[0])
+    assert int(np.abs(a.astype(np.int32)).max()) == 32767
