@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""Benchmark of the ids->waveform hot path (contract: see the task description / DESIGN.md §5).
+
+    python bench.py --gpus N --steps K --warmup W            # the CUDA engine (libm3b200)
+    python bench.py --impl reference --gpus N --steps K ...    # the CPU path (oracle port), rank 0 only
+
+Workload = BASELINE.json configs[2] (the one the metric is quoted on): an en_US/vctk_low-shaped
+voice (109 speakers, synthetic random weights -- no real voice is reachable offline), batch 256,
+80 ids per utterance, sid[b] = b mod 109, PCG64(1234); the batch is sharded by rows over the
+N ranks (strong scaling, no collective on the compute path).  A "step" = one pass of the hot
+path over the whole batch.  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+GLOBAL_BATCH = 256
+IDS_PER_UTT = 80
+N_SPEAKERS = 109
+NUM_SYMBOLS = 50
+VOICE_SEED = 22
+METRIC = "audio samples/s (en_US/vctk_low batch=256)"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def make_voice(root: Path) -> Path:
+    """Synthetic vctk_low-shaped voice; written by local rank 0, shared through the filesystem."""
+    from mimic3_b200 import synth_voice as sv
+    d = root / "en_US" / "vctk_low"
+    marker = d / ".complete"
+    if not marker.exists():
+        sv.write_voice(d, sv.low_config(n_speakers=N_SPEAKERS, num_symbols=NUM_SYMBOLS), seed=VOICE_SEED)
+        marker.write_text("ok")
+    return d
+
+
+def make_inputs(batch: int = GLOBAL_BATCH):
+    rng = np.random.Generator(np.random.PCG64(1234))
+    ids = rng.integers(4, NUM_SYMBOLS, size=(batch, IDS_PER_UTT)).astype(np.int64)  # pad/bos/eos/blank excluded
+    lengths = np.full(batch, IDS_PER_UTT, dtype=np.int64)
+    sid = (np.arange(batch) % N_SPEAKERS).astype(np.int64)
+    return ids, lengths, sid
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(gpu_index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:  # nvidia-smi missing
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def algorithmic_flops_per_frame(cfg) -> dict:
+    """SURVEY.md §8(d) general formula, per mel frame, from the voice's config."""
+    I = cfg.inter_channels
+    C0 = cfg.upsample_initial_channel
+    out = {"conv_pre": 2 * I * C0 * 7, "ups": 0, "mrf": 0}
+    L = 1
+    c = C0
+    for i, (u, k) in enumerate(zip(cfg.upsample_rates, cfg.upsample_kernel_sizes)):
+        cin, cout = c, c // 2
+        out["ups"] += 2 * cin * cout * k * L          # each input row touches k taps
+        L *= u
+        nconv = sum(len(d) * (2 if cfg.resblock == "1" else 1) for d in cfg.resblock_dilation_sizes) / len(cfg.resblock_kernel_sizes)
+        for rk, dil in zip(cfg.resblock_kernel_sizes, cfg.resblock_dilation_sizes):
+            out["mrf"] += 2 * cout * cout * rk * len(dil) * (2 if cfg.resblock == "1" else 1) * L
+        c = cout
+    out["post"] = 2 * c * 7 * L
+    Hf = cfg.hidden_channels
+    out["flow"] = 4 * 2 * ((I // 2) * Hf + 4 * (Hf * 2 * Hf * 5) + 3 * Hf * 2 * Hf + Hf * Hf + Hf * (I // 2))
+    return out
+
+
+def run_reference(args, rank: int, world: int):
+    """CPU arm: the oracle port (kind "port": onnxruntime + generator.onnx are unobtainable offline)
+    on rank 0's host cores, B=1 loop like the reference (voice.py:180-181), bounded sample per step."""
+    if rank != 0:
+        return
+    import torch
+    from oracle.vits_oracle import VitsOracle, audio_float_to_int16
+    with tempfile.TemporaryDirectory() as d:
+        vd = make_voice(Path(d))
+        orc = VitsOracle(str(vd))
+        ids, lengths, sid = make_inputs()
+        sample = max(1, args.ref_utts)
+        scales = orc.defaults
+        cores = torch.get_num_threads()
+
+        def step(k):
+            n = 0
+            for j in range(sample):
+                b = (k * sample + j) % GLOBAL_BATCH
+                n += audio_float_to_int16(orc.infer(ids[b], scales, sid=int(sid[b]), seed=1234, row=b)).size
+            return n
+        for k in range(args.warmup):
+            step(k)
+        t0 = time.perf_counter()
+        total = sum(step(args.warmup + k) for k in range(args.steps))
+        dt = time.perf_counter() - t0
+    value = total / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[2]: vctk_low-shaped synthetic voice, 109 speakers, batch=256 x 80 ids",
+                   "sample": f"{sample} utterances of the batch per step, batch-1 loop"},
+        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port",
+                         "sample": f"{sample} utterances/step x {args.steps} steps, torch fp32 CPU, {cores} threads"},
+        "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--ref-utts", type=int, default=32, help="utterances per step for the CPU arm")
+    ap.add_argument("--cpu-baseline-utts", type=int, default=64)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--deterministic", action="store_true", help="noise scales 0 (parity settings)")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the engine has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    distributed = world > 1
+    if distributed:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if args.gpus != world:
+        log(f"[bench] note: --gpus {args.gpus} but WORLD_SIZE {world}; using WORLD_SIZE")
+    from mimic3_b200.engine import B200Session, STAGES
+    from mimic3_b200 import synth_voice as sv
+
+    # -- voice: written once (rank 0), read by every rank ---------------------------------
+    shared = Path(os.environ.get("M3B200_BENCH_DIR", tempfile.gettempdir())) / f"m3b200_bench_voice_{os.environ.get('MASTER_PORT', 'single')}"
+    if local_rank == 0:
+        make_voice(shared)
+    if distributed:
+        dist.barrier()
+    vd = make_voice(shared)
+    sess = B200Session(str(vd), device=local_rank)
+    cfg = sv.low_config(n_speakers=N_SPEAKERS, num_symbols=NUM_SYMBOLS)
+    scales = (0.0, 1.0, 0.0) if args.deterministic else (sess.info.noise_scale, sess.info.length_scale, sess.info.noise_w)
+
+    # -- inputs: rank r owns rows [r*B/N, (r+1)*B/N) ------------------------------------------
+    ids, lengths, sid = make_inputs()
+    per = GLOBAL_BATCH // world
+    lo, hi = rank * per, (rank + 1) * per if rank < world - 1 else GLOBAL_BATCH
+    my_lengths, my_sid = lengths[lo:hi], sid[lo:hi]
+    if distributed:
+        # NCCL scatter of the padded id tensor from rank 0 (north_star: the only collectives on the
+        # path are the id scatter and the PCM gather)
+        chunks = None
+        if rank == 0:
+            full = torch.from_numpy(ids).cuda()
+            chunks = [full[r * per:(r + 1) * per if r < world - 1 else GLOBAL_BATCH].contiguous() for r in range(world)]
+        d_ids = torch.empty((hi - lo, IDS_PER_UTT), dtype=torch.int64, device="cuda")
+        if all(c.shape == d_ids.shape for c in (chunks or [d_ids])):
+            dist.scatter(d_ids, chunks, src=0)
+        else:  # ragged last shard
+            d_ids.copy_(torch.from_numpy(ids[lo:hi]))
+    else:
+        d_ids = torch.from_numpy(ids[lo:hi]).cuda()
+    h_ids = np.ascontiguousarray(ids[lo:hi])
+    torch.cuda.synchronize()
+
+    def step_resident(seed, timing=False):
+        return sess.infer(IDS_PER_UTT, my_lengths, scales, my_sid, seed=seed, host_copy=False,
+                          device_ids_ptr=d_ids.data_ptr(), stage_timing=timing)
+
+    def step_e2e(seed):
+        return sess.infer(h_ids, my_lengths, scales, my_sid, seed=seed)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if distributed:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for k in range(args.warmup):
+        step_resident(1000 + k)
+    # ---- timed region: device-resident inputs --------------------------------------------------
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    sync_all()
+    t0 = time.perf_counter()
+    samples = launches = 0
+    dev_ms = 0.0
+    frames = 0
+    for k in range(args.steps):
+        r = step_resident(2000 + k)
+        samples += r.total_samples
+        frames += int(r.frames.sum())
+        launches += r.launches
+        dev_ms += r.device_ms
+    sync_all()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop() if sampler else None
+
+    # ---- stage times (separate pass; event pairs around each stage on the engine's stream) -----
+    stage_ms = {s: 0.0 for s in STAGES}
+    st_frames = 0
+    for k in range(args.steps):
+        r = step_resident(2000 + k, timing=True)
+        st_frames += int(r.frames.sum())
+        for s in STAGES:
+            if "ms:" + s in r.tensors:
+                stage_ms[s] += float(r.tensors["ms:" + s][0, 0])
+
+    # ---- end to end through the public call: host ids in, int16 PCM back on the host -------------
+    for k in range(2):
+        step_e2e(3000 + k)
+    sync_all()
+    t1 = time.perf_counter()
+    e2e_samples = 0
+    for k in range(args.steps):
+        r = step_e2e(2000 + k)
+        e2e_samples += r.total_samples
+    sync_all()
+    e2e_wall = time.perf_counter() - t1
+
+    # ---- reduce over ranks: max time, summed samples ------------------------------------------------
+    vec = torch.tensor([wall, dev_ms / 1e3, e2e_wall], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor([samples, e2e_samples, launches, frames], dtype=torch.float64, device="cuda")
+    if distributed:
+        dist.all_reduce(vec, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    wall_max, dev_max, e2e_max = [float(x) for x in vec.tolist()]
+    tot_samples, tot_e2e, tot_launch, tot_frames = [float(x) for x in cnt.tolist()]
+
+    if rank == 0:
+        value = tot_samples / wall_max
+        fl = algorithmic_flops_per_frame(cfg)
+        mrf_ms = stage_ms["mrf"] / args.steps
+        mrf_flops = fl["mrf"] * (st_frames / args.steps)
+        peaks = {}
+        try:
+            peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+        except Exception:
+            pass
+        peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        achieved_tf = mrf_flops / (mrf_ms * 1e-3) / 1e12 if mrf_ms > 0 else 0.0
+        line = {
+            "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": wall_max / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "configs[2]: vctk_low-shaped synthetic voice (109 speakers, random weights), "
+                                   "global batch 256 x 80 ids, sid=b%109, rows sharded over ranks",
+                       "global_batch": GLOBAL_BATCH, "ids_per_utterance": IDS_PER_UTT,
+                       "scales": [float(s) for s in scales], "parallelism": f"batch-shard x{world}",
+                       "frames_per_step": tot_frames / args.steps, "samples_per_step": tot_samples / args.steps,
+                       "l2": "no flush: per-step activations (GBs) exceed the 126 MB L2 many times over",
+                       "timing": "wall clock between barrier+synchronize pairs (>= CUDA-event time), max over ranks",
+                       "device_event_ms_per_step": dev_max / args.steps * 1e3},
+            "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
+            "roofline": {"kernel": "MRF stage (resblock convs)", "bound": "tensor", "achieved": achieved_tf,
+                         "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf if peak_tf else None,
+                         "traffic": None,
+                         "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1400"},
+            "e2e": {"value": tot_e2e / e2e_max, "unit": "samples/s",
+                    "h2d_bytes_per_step": int(GLOBAL_BATCH * IDS_PER_UTT * 8 + GLOBAL_BATCH * 16),
+                    "d2h_bytes_per_step": int(tot_e2e / args.steps * 2)},
+            "gpu_launches": int(tot_launch),
+            "clocks": clocks,
+        }
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(vd, ids, sid, scales, args.cpu_baseline_utts)
+        print(json.dumps(line), flush=True)
+    if distributed:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def cpu_baseline(vd, ids, sid, scales, n_utts):
+    import torch
+    from oracle.vits_oracle import VitsOracle, audio_float_to_int16
+    orc = VitsOracle(str(vd))
+    orc.infer(ids[0, :20], scales, sid=0)  # warm-up
+    t0 = time.perf_counter()
+    n = 0
+    for b in range(n_utts):
+        n += audio_float_to_int16(orc.infer(ids[b], scales, sid=int(sid[b]), seed=1234, row=b)).size
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{n_utts} utterances of the batch, batch-1 loop, torch fp32 CPU ({dt:.1f} s)"}
+
+
+if __name__ == "__main__":
+    main()

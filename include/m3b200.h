@@ -33,6 +33,7 @@ extern "C" {
 #define M3_FLAG_DEBUG_TENSORS 2u  /* keep named intermediates (tests only; slow)           */
 #define M3_FLAG_DEVICE_IDS 4u     /* `ids` is device memory already (benchmark "resident") */
 #define M3_FLAG_NO_HOST_COPY 8u   /* leave PCM on the device; host pointers are NULL       */
+#define M3_FLAG_STAGE_TIMING 16u  /* CUDA-event time per stage, read back as tensors "ms:<stage>" */
 
 typedef struct m3_voice m3_voice;   /* loaded voice == the ORT session object (voice.py:77,83) */
 typedef struct m3_result m3_result; /* one run's outputs == ORT's returned arrays             */
@@ -89,6 +90,10 @@ int64_t m3_result_kernel_launches(const m3_result* r);        /* kernels this ca
 /* Debug intermediates (M3_FLAG_DEBUG_TENSORS): row-major float [rows][cols]; returns M3_ERR_INVALID if absent. */
 int32_t m3_result_tensor(const m3_result* r, const char* name, const float** data, int64_t* rows, int64_t* cols);
 void m3_result_free(m3_result* r);
+
+/* Diagnostics: runs test #which of the tcgen05/TMEM building blocks on the current device and
+ * stores the max abs error against a host reference (negative = CUDA error code). */
+int32_t m3_selftest(int32_t which, double* result);
 
 #ifdef __cplusplus
 }

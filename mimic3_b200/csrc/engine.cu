@@ -48,6 +48,7 @@ Context::Context(int dev) : device(dev) {
 }
 Context::~Context() {
   cudaSetDevice(device);
+  for (auto e : marks) cudaEventDestroy(e);
   if (ev0) cudaEventDestroy(ev0);
   if (ev1) cudaEventDestroy(ev1);
   if (stream) cudaStreamDestroy(stream);
@@ -328,6 +329,7 @@ std::unique_ptr<DeviceVoice> build_device_voice(const HostVoice& hv, int device)
     dv.dec_cond_off = add_cond("dec.cond", C0);
     const int nk = int(c.rb_kernels.size());
     dv.ups.resize(c.up_rates.size());
+    dv.rbs.resize(c.up_rates.size() * nk);
     for (size_t i = 0; i < c.up_rates.size(); ++i) {
       UpW& u = dv.ups[i];
       u.cin = C0 >> i;
@@ -352,23 +354,22 @@ std::unique_ptr<DeviceVoice> build_device_voice(const HostVoice& hv, int device)
       B.n_params += w.numel();
       B.vec(&u.b, "dec.ups." + std::to_string(i) + ".bias", u.cout);
       for (int j = 0; j < nk; ++j) {
-        ResBlockW rb;
+        // NOTE: Builder records the address of every pointer slot, so the Lin objects must
+        // already sit at their final address (pre-sized vectors, no copies afterwards).
+        ResBlockW& rb = dv.rbs[i * nk + j];
         rb.k = c.rb_kernels[j];
         rb.dil = c.rb_dils[j];
         const std::string rp = "dec.resblocks." + std::to_string(i * nk + j);
+        rb.c1.resize(rb.dil.size());
+        if (c.resblock != "2") rb.c2.resize(rb.dil.size());
         for (size_t d = 0; d < rb.dil.size(); ++d) {
-          Lin l1, l2;
           if (c.resblock == "2") {
-            B.conv(l1, rp + ".convs." + std::to_string(d), u.cout, u.cout, rb.k);
-            rb.c1.push_back(l1);
+            B.conv(rb.c1[d], rp + ".convs." + std::to_string(d), u.cout, u.cout, rb.k);
           } else {
-            B.conv(l1, rp + ".convs1." + std::to_string(d), u.cout, u.cout, rb.k);
-            B.conv(l2, rp + ".convs2." + std::to_string(d), u.cout, u.cout, rb.k);
-            rb.c1.push_back(l1);
-            rb.c2.push_back(l2);
+            B.conv(rb.c1[d], rp + ".convs1." + std::to_string(d), u.cout, u.cout, rb.k);
+            B.conv(rb.c2[d], rp + ".convs2." + std::to_string(d), u.cout, u.cout, rb.k);
           }
         }
-        dv.rbs.push_back(rb);
       }
     }
     const int cl = C0 >> c.up_rates.size();
@@ -450,6 +451,34 @@ struct Run {
   cudaStream_t st;
   Result* res;
   bool debug;
+  bool timing = false;
+  mutable std::vector<std::string> mark_names;
+
+  // stage boundary: time between consecutive marks is reported as "ms:<name of the later mark>"
+  void mark(const char* name) const {
+    if (!timing) return;
+    const size_t i = mark_names.size();
+    if (cx.marks.size() <= i) {
+      cudaEvent_t e;
+      M3_CUDA(cudaEventCreate(&e));
+      cx.marks.push_back(e);
+    }
+    M3_CUDA(cudaEventRecord(cx.marks[i], st));
+    mark_names.push_back(name);
+  }
+  void collect_marks() const {
+    if (!timing) return;
+    for (size_t i = 1; i < mark_names.size(); ++i) {
+      float ms = 0;
+      M3_CUDA(cudaEventElapsedTime(&ms, cx.marks[i - 1], cx.marks[i]));
+      DebugTensor& t = res->debug["ms:" + mark_names[i]];
+      if (t.data.empty()) {
+        t.rows = t.cols = 1;
+        t.data.assign(1, 0.f);
+      }
+      t.data[0] += ms;
+    }
+  }
 
   ConvParams base_conv(const Lin& l, const float* in, int in_stride, float* out, int out_stride, const Segs& s,
                        int scale) const {
@@ -552,6 +581,8 @@ Result* run_inference(Voice& v, const int64_t* ids, const int64_t* lengths, int 
   cudaStream_t st = cx.stream;
   g_launch_count = 0;
   Run R{dv, cx, st, res.get(), (flags & M3_FLAG_DEBUG_TENSORS) != 0};
+  R.timing = (flags & M3_FLAG_STAGE_TIMING) != 0;
+  R.mark("start");
 
   const int H = c.hidden, I = c.inter, Ff = c.filter, Fd = dv.dp_ch;
   const int G = c.gin;
@@ -634,6 +665,7 @@ Result* run_inference(Voice& v, const int64_t* ids, const int64_t* lengths, int 
     launch_layernorm(x, y, nullptr, L.g2, L.b2, x, NT, H, 0, st);
   }
   R.conv(R.base_conv(dv.enc_proj, x, H, stats, 2 * I, tok, 1), tok);
+  R.mark("text_encoder");
   R.dump("x", x, NT, H);
   R.dump("stats", stats, NT, 2 * I);
 
@@ -696,6 +728,7 @@ Result* run_inference(Voice& v, const int64_t* ids, const int64_t* lengths, int 
   R.dump("logw", logw, NT, 1);
 
   // ---------------- A.0 durations -> frames ----------------
+  R.mark("duration_predictor");
   int* cum = A.alloc<int>(NT);
   launch_durations(logw, 1, length_scale, cum, d_frm_len, d_tok_off, d_tok_len, batch, st);
   int* h_frames = hm + 2 * batch;
@@ -754,7 +787,9 @@ Result* run_inference(Voice& v, const int64_t* ids, const int64_t* lengths, int 
 
   // ---------------- length regulator + prior sample ----------------
   float* z = A2.alloc<float>(size_t(NF) * I);
+  R.mark("durations_sync");
   launch_expand(stats, I, cum, d_tok_off, d_tok_len, d_frm_off, d_frm_len, batch, Fmax, noise_scale, seed, z, st);
+  R.mark("expand");
   R.dump("z_p", z, NF, I);
 
   // ---------------- A.3 flow (reverse) ----------------
@@ -802,6 +837,7 @@ Result* run_inference(Voice& v, const int64_t* ids, const int64_t* lengths, int 
       }
     }
   }
+  R.mark("flow");
   R.dump("z", z, NF, I);
 
   // ---------------- A.4 HiFi-GAN ----------------
@@ -814,6 +850,7 @@ Result* run_inference(Voice& v, const int64_t* ids, const int64_t* lengths, int 
     }
     R.conv(p, frm);
   }
+  R.mark("conv_pre");
   int scale = 1;
   const int nk = int(c.rb_kernels.size());
   for (size_t i = 0; i < dv.ups.size(); ++i) {
@@ -849,6 +886,7 @@ Result* run_inference(Voice& v, const int64_t* ids, const int64_t* lengths, int 
       p.phases = u.u;
       launch_conv(p, batch, Fmax, st);
     }
+    R.mark("upsample");
     Segs lvl{d_frm_off, d_frm_len, batch, Fmax};
     for (int j = 0; j < nk; ++j) {
       const ResBlockW& rb = dv.rbs[i * nk + j];
@@ -892,6 +930,7 @@ Result* run_inference(Voice& v, const int64_t* ids, const int64_t* lengths, int 
         src = yb[d & 1];
       }
     }
+    R.mark("mrf");
     cur = sum;
     scale = out_scale;
     if (i == 0) R.dump("mrf0", sum, NF * out_scale, u.cout);
@@ -902,6 +941,7 @@ Result* run_inference(Voice& v, const int64_t* ids, const int64_t* lengths, int 
   M3_CUDA(cudaMemsetAsync(peak, 0, size_t(batch) * 4, st));
   launch_conv_post(cur, dv.post_c, dv.post_w, dv.post_k, 0.01f, audio, peak, d_frm_off, d_frm_len, hop, batch, Fmax, st);
   launch_to_int16(audio, peak, pcm, d_frm_off, d_frm_len, hop, batch, Fmax, st);
+  R.mark("post_int16");
 
   // ---------------- outputs ----------------
   const size_t NS = size_t(NF) * hop;
@@ -925,6 +965,7 @@ Result* run_inference(Voice& v, const int64_t* ids, const int64_t* lengths, int 
   M3_CUDA(cudaEventElapsedTime(&ms, cx.ev0, cx.ev1));
   res->device_ms = ms;
   res->launches = g_launch_count;
+  R.collect_marks();
   res->peaks.assign(h_peaks, h_peaks + batch);
   lease.keep = true;
   return res.release();

@@ -139,6 +139,7 @@ struct Context {  // per concurrent call: stream + workspaces (SURVEY.md §8b th
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   Arena a1, a2;
   PinnedBuf h_in, h_meta, h_pcm, h_audio;
+  std::vector<cudaEvent_t> marks;  // stage-timing events (M3_FLAG_STAGE_TIMING), created lazily
   explicit Context(int dev);
   ~Context();
 };

@@ -10,6 +10,7 @@
 namespace m3 {
 
 extern thread_local int64_t g_launch_count;  // kernels launched by this thread's current call
+void post_launch(const char* what, cudaStream_t st);
 
 struct ConvParams {
   // input

@@ -5,6 +5,8 @@
 #include <cfloat>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
+#include <stdexcept>
 
 #include "kernels.h"
 
@@ -12,7 +14,22 @@ namespace m3 {
 
 thread_local int64_t g_launch_count = 0;
 
-#define M3_LAUNCHED() (++g_launch_count)
+// Counts the launch; with M3B200_SYNC_DEBUG=1 also synchronises and names the failing kernel.
+void post_launch(const char* what, cudaStream_t st) {
+  ++g_launch_count;
+  static const bool dbg = [] {
+    const char* e = getenv("M3B200_SYNC_DEBUG");
+    return e && *e && *e != '0';
+  }();
+  cudaError_t err = cudaGetLastError();
+  if (err == cudaSuccess && dbg) err = cudaStreamSynchronize(st);
+  if (err != cudaSuccess) {
+    char buf[256];
+    snprintf(buf, sizeof buf, "kernel %s failed: %s", what, cudaGetErrorString(err));
+    throw std::runtime_error(buf);
+  }
+}
+#define M3_LAUNCHED() post_launch(__func__, st)
 
 // -------------------------------------------------------------------------------------
 // Philox4x32-10 noise source; specification in oracle/philox.py (kept bit-compatible).

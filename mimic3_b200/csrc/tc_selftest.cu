@@ -1,0 +1,170 @@
+// Self-test of the tcgen05 building blocks (descriptor conventions, row-shifted A operand,
+// TMEM st / accumulate-on-top / ld) against a host reference.  Exposed as m3_selftest();
+// run by tests/test_gpu_tc.py so a descriptor mistake is caught in isolation.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdlib>
+#include <vector>
+
+#include "../../include/m3b200.h"
+#include "tc_common.cuh"
+
+namespace m3 {
+namespace {
+
+template <int FMT>
+__global__ void __launch_bounds__(128) tc_probe_kernel(const float* __restrict__ A, const float* __restrict__ W,
+                                                       const float* __restrict__ init, float* __restrict__ D, int K,
+                                                       int N, int taps, int dil, int rows, uint32_t lboA,
+                                                       uint32_t sboA, uint32_t lboB, uint32_t sboB) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  using E = tc::Elem<FMT>;
+  __shared__ uint32_t tmem_slot;
+  __shared__ __align__(8) uint64_t bar;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint32_t* sA = reinterpret_cast<uint32_t*>(smem);                      // [K/8][rows][8] elements
+  uint32_t* sW = reinterpret_cast<uint32_t*>(smem + size_t(K / 8) * rows * 16);  // [taps][K/8][N][8]
+
+  for (int idx = tid; idx < rows * (K / 2); idx += 128) {
+    const int r = idx / (K / 2), k2 = idx - r * (K / 2);
+    const int k = k2 * 2;
+    const uint32_t v = E::pack2(A[r * K + k], A[r * K + k + 1]);
+    sA[((k >> 3) * rows + r) * 4 + ((k & 7) >> 1)] = v;
+  }
+  for (int idx = tid; idx < taps * N * (K / 2); idx += 128) {
+    const int tap = idx / (N * (K / 2));
+    const int rem = idx - tap * N * (K / 2);
+    const int n = rem / (K / 2), k = (rem - n * (K / 2)) * 2;
+    const uint32_t v = E::pack2(W[(tap * N + n) * K + k], W[(tap * N + n) * K + k + 1]);
+    sW[((tap * (K / 8) + (k >> 3)) * N + n) * 4 + ((k & 7) >> 1)] = v;
+  }
+  if (warp == 0) tc::tmem_alloc<256>(&tmem_slot);
+  if (tid == 0) {
+    tc::mbar_init(&bar, 1);
+    tc::mbar_fence_init();
+  }
+  tc::fence_async_smem();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t trow = tmem + (uint32_t(warp * 32) << 16);
+
+  if (init) {  // pre-load the accumulator: the MMAs must add on top of it
+    for (int c0 = 0; c0 < N; c0 += 16) {
+      float v[16];
+      for (int j = 0; j < 16; ++j) v[j] = init[(warp * 32 + lane) * N + c0 + j];
+      tc::tmem_st16(trow + c0, v);
+    }
+    tc::tmem_st_wait();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+  }
+
+  if (tid == 0) {
+    const uint32_t idesc = tc::make_idesc(128, N, FMT);
+    const uint32_t aBase = tc::smem_u32(sA), wBase = tc::smem_u32(sW);
+    uint32_t acc = init ? 1u : 0u;
+    for (int tap = 0; tap < taps; ++tap) {
+      for (int ks = 0; ks < K / 16; ++ks) {
+        const uint64_t ad = tc::make_desc(aBase + uint32_t(tap * dil) * 16u + uint32_t(ks) * 2u * uint32_t(rows) * 16u, lboA, sboA);
+        const uint64_t bd = tc::make_desc(wBase + uint32_t(tap * (K / 8) + ks * 2) * uint32_t(N) * 16u, lboB, sboB);
+        tc::mma_f16_ss(tmem, ad, bd, idesc, acc);
+        acc = 1u;
+      }
+    }
+    tc::mma_commit(&bar);
+  }
+  tc::mbar_wait(&bar, 0);
+  tc::fence_after_sync();
+  for (int c0 = 0; c0 < N; c0 += 16) {
+    float v[16];
+    tc::tmem_ld16(trow + c0, v);
+    tc::tmem_ld_wait();
+    for (int j = 0; j < 16; ++j) D[(warp * 32 + lane) * N + c0 + j] = v[j];
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc<256>(tmem);
+}
+
+double run_probe(int fmt, int K, int N, int taps, int dil, bool with_init, bool swap_lbo_sbo) {
+  const int rows = 128 + (taps - 1) * dil;
+  std::vector<float> A(size_t(rows) * K), W(size_t(taps) * N * K), I(size_t(128) * N), D(size_t(128) * N);
+  uint32_t s = 12345u + K * 7 + N * 13 + taps;
+  auto rnd = [&]() {
+    s = s * 1664525u + 1013904223u;
+    return float(int((s >> 9) & 0xFFFF) - 32768) / 32768.0f;
+  };
+  auto q = [&](float x) { return fmt == 1 ? tc::Elem<1>::round(x) : tc::Elem<0>::round(x); };
+  for (auto& v : A) v = q(rnd());
+  for (auto& v : W) v = q(rnd() * 0.25f);
+  for (auto& v : I) v = rnd() * 3.0f;
+  float *dA, *dW, *dI, *dD;
+  cudaMalloc(&dA, A.size() * 4);
+  cudaMalloc(&dW, W.size() * 4);
+  cudaMalloc(&dI, I.size() * 4);
+  cudaMalloc(&dD, D.size() * 4);
+  cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice);
+  cudaMemcpy(dW, W.data(), W.size() * 4, cudaMemcpyHostToDevice);
+  cudaMemcpy(dI, I.data(), I.size() * 4, cudaMemcpyHostToDevice);
+  cudaMemset(dD, 0, D.size() * 4);
+  uint32_t lboA = rows * 16, sboA = 128, lboB = N * 16, sboB = 128;
+  if (swap_lbo_sbo) {
+    std::swap(lboA, sboA);
+    std::swap(lboB, sboB);
+  }
+  const size_t smem = size_t(K / 8) * rows * 16 + size_t(taps) * (K / 8) * N * 16;
+  double err = 1e30;
+  cudaError_t e;
+  if (smem > 227 * 1024) return -1000.0;
+  if (fmt == 1) {
+    cudaFuncSetAttribute(tc_probe_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    tc_probe_kernel<1><<<1, 128, smem>>>(dA, dW, with_init ? dI : nullptr, dD, K, N, taps, dil, rows, lboA, sboA, lboB, sboB);
+  } else {
+    cudaFuncSetAttribute(tc_probe_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    tc_probe_kernel<0><<<1, 128, smem>>>(dA, dW, with_init ? dI : nullptr, dD, K, N, taps, dil, rows, lboA, sboA, lboB, sboB);
+  }
+  e = cudaDeviceSynchronize();
+  if (e == cudaSuccess) {
+    cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost);
+    err = 0;
+    for (int m = 0; m < 128; ++m)
+      for (int n = 0; n < N; ++n) {
+        double acc = with_init ? I[size_t(m) * N + n] : 0.0;
+        for (int tap = 0; tap < taps; ++tap)
+          for (int k = 0; k < K; ++k) acc += double(A[size_t(m + tap * dil) * K + k]) * W[(size_t(tap) * N + n) * K + k];
+        err = std::fmax(err, std::fabs(acc - D[size_t(m) * N + n]));
+      }
+  } else {
+    err = -double(int(e));
+    cudaGetLastError();
+  }
+  cudaFree(dA);
+  cudaFree(dW);
+  cudaFree(dI);
+  cudaFree(dD);
+  return err;
+}
+
+}  // namespace
+}  // namespace m3
+
+extern "C" int32_t m3_selftest(int32_t which, double* result) {
+  if (!result) return M3_ERR_INVALID;
+  using m3::run_probe;
+  switch (which) {
+    case 0: *result = run_probe(1, 32, 32, 3, 1, false, false); break;    // bf16, MRF stage-3 shape
+    case 1: *result = run_probe(1, 64, 64, 7, 12, false, false); break;   // dilated k=7
+    case 2: *result = run_probe(1, 128, 128, 5, 6, true, false); break;   // accumulate on top of tcgen05.st
+    case 3: *result = run_probe(0, 32, 32, 3, 2, true, false); break;     // fp16 operands
+    case 4: *result = run_probe(1, 192, 256, 2, 1, false, false); break;  // flow WN in_layer shape (N=256)
+    case 5: *result = run_probe(1, 32, 32, 3, 1, false, true); break;     // diagnostic: LBO/SBO swapped
+    case 6: *result = run_probe(1, 96, 192, 1, 1, false, false); break;   // 1x1 conv
+    case 7: *result = run_probe(0, 64, 64, 7, 3, true, false); break;
+    default: return M3_ERR_INVALID;
+  }
+  return M3_OK;
+}

@@ -17,7 +17,9 @@ from typing import Dict, List, Optional, Sequence
 import numpy as np
 
 M3_OK, M3_ERR_INVALID, M3_ERR_IO, M3_ERR_MODEL, M3_ERR_CUDA, M3_ERR_NOGPU = range(6)
-FLAG_KEEP_FLOAT, FLAG_DEBUG_TENSORS, FLAG_DEVICE_IDS, FLAG_NO_HOST_COPY = 1, 2, 4, 8
+FLAG_KEEP_FLOAT, FLAG_DEBUG_TENSORS, FLAG_DEVICE_IDS, FLAG_NO_HOST_COPY, FLAG_STAGE_TIMING = 1, 2, 4, 8, 16
+STAGES = ("text_encoder", "duration_predictor", "durations_sync", "expand", "flow", "conv_pre", "upsample", "mrf",
+          "post_int16")
 
 _LIB_NAME = "libm3b200.so"
 _lib = None
@@ -29,7 +31,7 @@ API_SYMBOLS = [
     "m3_voice_get_info", "m3_infer", "m3_result_batch", "m3_result_sample_offsets",
     "m3_result_num_frames", "m3_result_pcm", "m3_result_audio", "m3_result_peaks",
     "m3_result_device_pcm", "m3_result_device_ms", "m3_result_kernel_launches",
-    "m3_result_tensor", "m3_result_free",
+    "m3_result_tensor", "m3_result_free", "m3_selftest",
 ]
 
 
@@ -92,6 +94,8 @@ def load_library() -> C.CDLL:
         lib.m3_result_tensor.argtypes = [vp, C.c_char_p, C.POINTER(C.POINTER(C.c_float)), i64p, i64p]
         lib.m3_result_free.restype = None
         lib.m3_result_free.argtypes = [vp]
+        lib.m3_selftest.restype = i32
+        lib.m3_selftest.argtypes = [i32, C.POINTER(C.c_double)]
         _lib = lib
         return lib
 
@@ -154,7 +158,7 @@ class B200Session:
     def infer(self, ids: np.ndarray, lengths: np.ndarray, scales: Sequence[float],
               sid: Optional[np.ndarray] = None, seed: int = 0, keep_float: bool = False,
               debug_tensors: Sequence[str] = (), host_copy: bool = True,
-              device_ids_ptr: Optional[int] = None) -> InferenceResult:
+              device_ids_ptr: Optional[int] = None, stage_timing: bool = False) -> InferenceResult:
         lengths = np.ascontiguousarray(lengths, dtype=np.int64)
         batch = int(lengths.shape[0])
         flags = 0
@@ -179,6 +183,9 @@ class B200Session:
             flags |= FLAG_KEEP_FLOAT
         if debug_tensors:
             flags |= FLAG_DEBUG_TENSORS
+        if stage_timing:
+            flags |= FLAG_STAGE_TIMING
+            debug_tensors = tuple(debug_tensors) + tuple("ms:" + s for s in STAGES)
         if not host_copy:
             flags |= FLAG_NO_HOST_COPY
         res = C.c_void_p()

@@ -156,8 +156,8 @@ def make_params(cfg: SynthModelConfig, seed: int = 0) -> Dict[str, np.ndarray]:
         # logw = (z0 - m0) * exp(-logs0): centre durations around ~3 frames / id
         # (constants chosen empirically for these random weights)
         if H >= 128:
-            P["dp.flows.0.m"] = np.array([[-1.5], [0.2]], dtype=np.float32)
-            P["dp.flows.0.logs"] = np.array([[-0.916], [-0.1]], dtype=np.float32)
+            P["dp.flows.0.m"] = np.array([[-6.0], [0.2]], dtype=np.float32)
+            P["dp.flows.0.logs"] = np.array([[1.5], [-0.1]], dtype=np.float32)
         else:
             P["dp.flows.0.m"] = np.array([[-1.6], [0.2]], dtype=np.float32)
             P["dp.flows.0.logs"] = np.array([[0.0], [-0.1]], dtype=np.float32)
