@@ -160,7 +160,7 @@ extern "C" int32_t m3_selftest(int32_t which, double* result) {
     case 1: *result = run_probe(1, 64, 64, 7, 12, false, false); break;   // dilated k=7
     case 2: *result = run_probe(1, 128, 128, 5, 6, true, false); break;   // accumulate on top of tcgen05.st
     case 3: *result = run_probe(0, 32, 32, 3, 2, true, false); break;     // fp16 operands
-    case 4: *result = run_probe(1, 192, 256, 2, 1, false, false); break;  // flow WN in_layer shape (N=256)
+    case 4: *result = run_probe(1, 192, 256, 1, 1, false, false); break;  // flow WN in_layer shape (N=256)
     case 5: *result = run_probe(1, 32, 32, 3, 1, false, true); break;     // diagnostic: LBO/SBO swapped
     case 6: *result = run_probe(1, 96, 192, 1, 1, false, false); break;   // 1x1 conv
     case 7: *result = run_probe(0, 64, 64, 7, 3, true, false); break;

@@ -7,7 +7,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 CASES = {0: "bf16 K32 N32 k3", 1: "bf16 K64 N64 k7 d12", 2: "bf16 K128 N128 k5 d6 +init",
-         3: "fp16 K32 N32 k3 d2 +init", 4: "bf16 K192 N256 k2", 6: "bf16 K96 N192 1x1",
+         3: "fp16 K32 N32 k3 d2 +init", 4: "bf16 K192 N256 1x1", 6: "bf16 K96 N192 1x1",
          7: "fp16 K64 N64 k7 d3 +init"}
 
 
