@@ -179,6 +179,8 @@ def main():
     ap.add_argument("--cpu-baseline-utts", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--deterministic", action="store_true", help="noise scales 0 (parity settings)")
+    ap.add_argument("--batch", type=int, default=GLOBAL_BATCH, help="global batch override (profiling runs only)")
+    ap.add_argument("--profile-only", action="store_true", help="skip stage/e2e/cpu passes (ncu runs)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -214,9 +216,10 @@ def main():
     scales = (0.0, 1.0, 0.0) if args.deterministic else (sess.info.noise_scale, sess.info.length_scale, sess.info.noise_w)
 
     # -- inputs: rank r owns rows [r*B/N, (r+1)*B/N) ------------------------------------------
-    ids, lengths, sid = make_inputs()
-    per = GLOBAL_BATCH // world
-    lo, hi = rank * per, (rank + 1) * per if rank < world - 1 else GLOBAL_BATCH
+    GB = args.batch
+    ids, lengths, sid = make_inputs(GB)
+    per = GB // world
+    lo, hi = rank * per, (rank + 1) * per if rank < world - 1 else GB
     my_lengths, my_sid = lengths[lo:hi], sid[lo:hi]
     if distributed:
         # NCCL scatter of the padded id tensor from rank 0 (north_star: the only collectives on the
@@ -224,7 +227,7 @@ def main():
         chunks = None
         if rank == 0:
             full = torch.from_numpy(ids).cuda()
-            chunks = [full[r * per:(r + 1) * per if r < world - 1 else GLOBAL_BATCH].contiguous() for r in range(world)]
+            chunks = [full[r * per:(r + 1) * per if r < world - 1 else GB].contiguous() for r in range(world)]
         d_ids = torch.empty((hi - lo, IDS_PER_UTT), dtype=torch.int64, device="cuda")
         if all(c.shape == d_ids.shape for c in (chunks or [d_ids])):
             dist.scatter(d_ids, chunks, src=0)
@@ -270,6 +273,11 @@ def main():
     # ---- stage times (separate pass; event pairs around each stage on the engine's stream) -----
     stage_ms = {s: 0.0 for s in STAGES}
     st_frames = 0
+    if args.profile_only:
+        if rank == 0:
+            print(json.dumps({"profile_only": True, "samples_per_step": samples / args.steps,
+                              "ms_per_step": wall / args.steps * 1e3}), flush=True)
+        return
     for k in range(args.steps):
         r = step_resident(2000 + k, timing=True)
         st_frames += int(r.frames.sum())
@@ -313,10 +321,12 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": wall_max / args.steps * 1e3, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "scaling": "strong", "vs_baseline": None,
+            "dtype": "bf16 tensor-core operands + fp32 accumulate/residual (decoder); f32 (text encoder, durations, flow)",
+            "data": "synthetic",
             "config": {"workload": "configs[2]: vctk_low-shaped synthetic voice (109 speakers, random weights), "
                                    "global batch 256 x 80 ids, sid=b%109, rows sharded over ranks",
-                       "global_batch": GLOBAL_BATCH, "ids_per_utterance": IDS_PER_UTT,
+                       "global_batch": GB, "ids_per_utterance": IDS_PER_UTT,
                        "scales": [float(s) for s in scales], "parallelism": f"batch-shard x{world}",
                        "frames_per_step": tot_frames / args.steps, "samples_per_step": tot_samples / args.steps,
                        "l2": "no flush: per-step activations (GBs) exceed the 126 MB L2 many times over",
@@ -328,7 +338,7 @@ def main():
                          "traffic": None,
                          "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1400"},
             "e2e": {"value": tot_e2e / e2e_max, "unit": "samples/s",
-                    "h2d_bytes_per_step": int(GLOBAL_BATCH * IDS_PER_UTT * 8 + GLOBAL_BATCH * 16),
+                    "h2d_bytes_per_step": int(GB * IDS_PER_UTT * 8 + GB * 16),
                     "d2h_bytes_per_step": int(tot_e2e / args.steps * 2)},
             "gpu_launches": int(tot_launch),
             "clocks": clocks,

@@ -7,6 +7,9 @@
 #include <cmath>
 #include <cstring>
 
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
 #include "../../include/m3b200.h"
 #include "kernels.h"
 
@@ -68,10 +71,9 @@ void Voice::release(Context* c) {
   idle.push_back(c);
 }
 DeviceVoice::~DeviceVoice() {
-  if (slab) {
-    cudaSetDevice(device);
-    cudaFree(slab);
-  }
+  if (slab || slab16) cudaSetDevice(device);
+  if (slab) cudaFree(slab);
+  if (slab16) cudaFree(slab16);
 }
 
 // ======================================================================================
@@ -385,6 +387,67 @@ std::unique_ptr<DeviceVoice> build_device_voice(const HostVoice& hv, int device)
     B.n_params += pw.numel();
   }
 
+  // ---- tensor-core operands of the MRF stages: per conv [tap][Cin/8][Cout][8], 16-bit
+  std::vector<uint16_t> h16;
+  {
+    const char* fe = getenv("M3B200_TC_FORMAT");
+    dv.tc_fmt = (fe && std::string(fe) == "fp16") ? 0 : 1;
+    const char* fs = getenv("M3B200_FORCE_SIMT");
+    dv.use_tc = !(fs && *fs && *fs != '0');
+    auto cvt = [&](float f) -> uint16_t {
+      if (dv.tc_fmt == 1) {
+        __nv_bfloat16 h = __float2bfloat16_rn(f);
+        return *reinterpret_cast<uint16_t*>(&h);
+      }
+      __half h = __float2half_rn(f);
+      return *reinterpret_cast<uint16_t*>(&h);
+    };
+    const int nk = int(c.rb_kernels.size());
+    dv.mrf.resize(c.up_rates.size());
+    for (size_t i = 0; i < c.up_rates.size(); ++i) {
+      MrfStageW& ms = dv.mrf[i];
+      const int C = c.up_init >> (i + 1);
+      int ks[4] = {0, 0, 0, 0};
+      int nd = nk ? int(c.rb_dils[0].size()) : 0;
+      bool uniform = c.resblock == "2" && nk <= 4;
+      for (int j = 0; j < nk && j < 4; ++j) {
+        ks[j] = c.rb_kernels[j];
+        if (int(c.rb_dils[j].size()) != nd) uniform = false;
+      }
+      int HX = 0, HY = 0;
+      for (int j = 0; j < nk && uniform; ++j) {
+        HX = std::max(HX, c.rb_dils[j][0] * (c.rb_kernels[j] - 1) / 2);
+        if (nd > 1) HY = std::max(HY, c.rb_dils[j][1] * (c.rb_kernels[j] - 1) / 2);
+      }
+      if (!uniform || !mrf_tc_supported(C, nk, nd, ks, std::max(HX, HY))) continue;
+      ms.ok = true;
+      ms.nk = nk;
+      ms.nd = nd;
+      ms.HX = HX;
+      ms.HY = HY;
+      ms.H = HY;
+      std::vector<float> late(C, 0.f);
+      for (int j = 0; j < nk; ++j)
+        for (int d = 0; d < nd; ++d) {
+          const std::string nm = "dec.resblocks." + std::to_string(i * nk + j) + ".convs." + std::to_string(d);
+          const int k = c.rb_kernels[j];
+          const OnnxTensor& w = hv.need(nm + ".weight", {C, C, k});
+          const OnnxTensor& bsrc = hv.need(nm + ".bias", {C});
+          if (d >= 1)
+            for (int ch = 0; ch < C; ++ch) late[ch] += bsrc.f32[ch];
+          while (h16.size() % 64) h16.push_back(0);
+          ms.woff[j][d] = h16.size();
+          const size_t o = h16.size();
+          h16.resize(o + size_t(k) * C * C);
+          for (int tap = 0; tap < k; ++tap)
+            for (int ci = 0; ci < C; ++ci)
+              for (int co = 0; co < C; ++co)
+                h16[o + ((size_t(tap) * (C / 8) + ci / 8) * C + co) * 8 + (ci & 7)] = cvt(w.f32[(size_t(co) * C + ci) * k + tap]);
+        }
+      B.place(&ms.late_bias, late);
+    }
+  }
+
   // ---- conditioning GEMM [G][n_cond]
   if (G && !cond_layers.empty()) {
     int n = 0;
@@ -430,6 +493,10 @@ std::unique_ptr<DeviceVoice> build_device_voice(const HostVoice& hv, int device)
   M3_CUDA(cudaMemcpy(dv.slab, B.pk.host.data(), dv.slab_floats * sizeof(float), cudaMemcpyHostToDevice));
   for (auto& f : B.fix) *f.slot = dv.slab + f.off;
   dv.n_params = B.n_params;
+  if (!h16.empty()) {
+    M3_CUDA(cudaMalloc(&dv.slab16, h16.size() * sizeof(uint16_t)));
+    M3_CUDA(cudaMemcpy(dv.slab16, h16.data(), h16.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+  }
   return dvp;
 }
 
@@ -888,6 +955,33 @@ Result* run_inference(Voice& v, const int64_t* ids, const int64_t* lengths, int 
     }
     R.mark("upsample");
     Segs lvl{d_frm_off, d_frm_len, batch, Fmax};
+    const MrfStageW& ms = dv.mrf[i];
+    if (dv.use_tc && ms.ok) {
+      MrfParams mp;
+      mp.x = xu;
+      mp.out = sum;
+      mp.w16 = dv.slab16;
+      mp.nk = ms.nk;
+      mp.nd = ms.nd;
+      for (int j = 0; j < ms.nk; ++j) {
+        const ResBlockW& rb = dv.rbs[i * nk + j];
+        mp.k[j] = rb.k;
+        for (int d = 0; d < ms.nd; ++d) {
+          mp.dil[j][d] = rb.dil[d];
+          mp.woff[j][d] = ms.woff[j][d];
+          mp.bias[j][d] = rb.c1[d].b;
+        }
+      }
+      mp.late_bias = ms.late_bias;
+      mp.seg_off = d_frm_off;
+      mp.seg_len = d_frm_len;
+      mp.scale = out_scale;
+      mp.H = ms.H;
+      mp.HX = ms.HX;
+      mp.HY = ms.HY;
+      mp.inv_nk = 1.0f / float(ms.nk);
+      launch_mrf_tc(mp, u.cout, dv.tc_fmt, batch, Fmax, st);
+    } else
     for (int j = 0; j < nk; ++j) {
       const ResBlockW& rb = dv.rbs[i * nk + j];
       const float* src = xu;
@@ -933,7 +1027,7 @@ Result* run_inference(Voice& v, const int64_t* ids, const int64_t* lengths, int 
     R.mark("mrf");
     cur = sum;
     scale = out_scale;
-    if (i == 0) R.dump("mrf0", sum, NF * out_scale, u.cout);
+    if (R.debug) R.dump(("mrf" + std::to_string(i)).c_str(), sum, NF * out_scale, u.cout);
   }
   float* audio = A2.alloc<float>(size_t(NF) * hop);
   int16_t* pcm = A2.alloc<int16_t>(size_t(NF) * hop);

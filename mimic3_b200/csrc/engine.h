@@ -68,10 +68,21 @@ struct ResBlockW {
   std::vector<Lin> c1, c2;  // c2 empty for resblock "2"
 };
 
+struct MrfStageW {  // tensor-core packing of one MRF stage (kernels_tc.cu)
+  bool ok = false;
+  unsigned long long woff[4][2] = {};
+  const float* late_bias = nullptr;
+  int H = 0, HX = 0, HY = 0, nk = 0, nd = 0;
+};
+
 struct DeviceVoice {
   VoiceConfig cfg;
   int device = 0;
   float* slab = nullptr;  // all weights, one allocation
+  uint16_t* slab16 = nullptr;  // 16-bit tensor-core operands
+  int tc_fmt = 1;              // 0 fp16, 1 bf16
+  bool use_tc = true;
+  std::vector<MrfStageW> mrf;
   size_t slab_floats = 0;
   int64_t n_params = 0;
   bool has_emb_g = false;

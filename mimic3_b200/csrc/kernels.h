@@ -47,6 +47,28 @@ struct ConvParams {
 
 void launch_conv(const ConvParams& p, int n_seg, int max_seg_len, cudaStream_t st);
 
+// Fused tensor-core MRF stage (kernels_tc.cu).  Weights: 16-bit, per conv [tap][Cin/8][Cout][8].
+struct MrfParams {
+  const float* x = nullptr;  // [rows][C] fp32, channels-last
+  float* out = nullptr;      // [rows][C] fp32
+  const uint16_t* w16 = nullptr;
+  unsigned long long woff[4][2] = {};  // element offset of conv (resblock j, conv d) in w16
+  const float* bias[4][2] = {};
+  const float* late_bias = nullptr;    // [C] = sum_j sum_{d>=1} bias[j][d]
+  int k[4] = {}, dil[4][2] = {};
+  int nk = 0, nd = 0;
+  const int* seg_off = nullptr;
+  const int* seg_len = nullptr;
+  int scale = 1;
+  int stride = 0;  // filled by the launcher: R - 2H
+  int H = 0, HX = 0, HY = 0;
+  int wg = 1;      // taps per weight-staging group (launcher)
+  float inv_nk = 1.f;
+};
+bool mrf_tc_supported(int C, int nk, int nd, const int* k, int max_halo);
+// fmt: 0 = fp16 operands, 1 = bf16 operands
+void launch_mrf_tc(const MrfParams& p, int C, int fmt, int n_seg, int max_len, cudaStream_t st);
+
 // out = res + act(LN(a + b)) over channels, eps 1e-5; act: 0 none, 1 erf-GELU
 void launch_layernorm(const float* a, const float* b, const float* res, const float* gamma, const float* beta,
                       float* out, int rows, int C, int act, cudaStream_t st);

@@ -1,0 +1,285 @@
+// tcgen05 tensor-core kernels (sm_100a).  Operands: bf16 or fp16 in the interleaved
+// no-swizzle layout of tc_common.cuh; accumulators and the residual stream: fp32 in TMEM.
+#include <cstdio>
+#include <stdexcept>
+
+#include "kernels.h"
+#include "tc_common.cuh"
+
+namespace m3 {
+
+// =====================================================================================
+// Fused MRF stage of the HiFi-GAN generator:
+//     out = 1/nk * sum_j ResBlock2_j(x),   ResBlock2(x): for d: x = x + conv_d(lrelu(x, 0.1))
+//
+// One CTA owns a window of R = NT*128 consecutive samples of one utterance:
+//   * lrelu(x) of the window (+halo) is staged once in smem as the MMA A operand (bufX);
+//   * per resblock the residual stream lives in TMEM: T <- x + b1 (tcgen05.st), the first
+//     conv's taps are tcgen05.mma's accumulating ON TOP of it (residual add for free), the
+//     epilogue reads T, writes lrelu(T) as bf16 into bufY, the second conv accumulates into
+//     the same T, and T is folded into the running sum S (also TMEM);
+//   * a conv tap is the same smem tile with the descriptor start advanced by tap*dil rows.
+// Only rows [H, R-H) of a window are exact after the second conv (H = its halo); windows
+// therefore advance by R - 2H.  Rows outside the utterance are zeroed in bufX/bufY, which
+// reproduces the reference's per-layer zero padding (batch-1 edge semantics).
+// =====================================================================================
+template <int C, int NT, int FMT>
+__global__ void __launch_bounds__(256, (C == 32 || (C == 64 && NT <= 2)) ? 2 : 1) mrf_tc_kernel(MrfParams p) {
+  constexpr int R = NT * 128;
+  constexpr int CH = C / 8;        // 16-byte K-chunks per row
+  constexpr int HC = C / 2;        // columns per epilogue thread (two column halves)
+  constexpr int TCOLS_RAW = 2 * NT * C;
+  constexpr int TCOLS = TCOLS_RAW <= 32 ? 32 : TCOLS_RAW <= 64 ? 64 : TCOLS_RAW <= 128 ? 128 : TCOLS_RAW <= 256 ? 256 : 512;
+  static_assert(TCOLS_RAW <= 512, "TMEM budget");
+  using E = tc::Elem<FMT>;
+
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint32_t tmem_slot;
+  __shared__ __align__(8) uint64_t bar;
+
+  const int seg = blockIdx.y;
+  const int L = p.seg_len[seg] * p.scale;
+  const int o0 = blockIdx.x * p.stride;
+  if (o0 >= L) return;
+  const long long base = (long long)p.seg_off[seg] * p.scale;
+  const int w0 = o0 - p.H;
+  const int ROWSX = R + 2 * p.HX, ROWSY = R + 2 * p.HY;
+  uint8_t* bufX = smem;
+  uint8_t* bufY = bufX + size_t(CH) * ROWSX * 16;
+  uint8_t* wbuf = bufY + size_t(CH) * ROWSY * 16;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q = warp & 3, hhalf = warp >> 2;
+  const float* __restrict__ xg = p.x;
+
+  if (warp == 0) tc::tmem_alloc<TCOLS>(&tmem_slot);
+  if (tid == 0) {
+    tc::mbar_init(&bar, 1);
+    tc::mbar_fence_init();
+  }
+  // ---- stage lrelu(x) of the window (+halo) as the A operand -------------------------
+  for (int idx = tid; idx < CH * ROWSX; idx += 256) {
+    const int c8 = idx / ROWSX, rr = idx - c8 * ROWSX;
+    const int g = w0 - p.HX + rr;
+    uint4 pk = make_uint4(0u, 0u, 0u, 0u);
+    if (g >= 0 && g < L) {
+      const float4 a = *reinterpret_cast<const float4*>(xg + (base + g) * C + c8 * 8);
+      const float4 b = *reinterpret_cast<const float4*>(xg + (base + g) * C + c8 * 8 + 4);
+      auto lr = [](float v) { return v >= 0.f ? v : 0.1f * v; };
+      pk.x = E::pack2(lr(a.x), lr(a.y));
+      pk.y = E::pack2(lr(a.z), lr(a.w));
+      pk.z = E::pack2(lr(b.x), lr(b.y));
+      pk.w = E::pack2(lr(b.z), lr(b.w));
+    }
+    *reinterpret_cast<uint4*>(bufX + size_t(idx) * 16) = pk;
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t lane_base = tmem + (uint32_t(q * 32) << 16);
+  const uint32_t T0 = 0, S0 = NT * C;  // column offsets of the two TMEM regions
+  const uint32_t idesc = tc::make_idesc(128, C, FMT);
+  uint32_t phase = 0;
+
+  for (int j = 0; j < p.nk; ++j) {
+    const int k = p.k[j];
+    const int half = (k - 1) / 2;
+    // ---- T <- x + bias of the first conv -------------------------------------------------
+    {
+      const float* __restrict__ b0 = p.bias[j][0];
+#pragma unroll 1
+      for (int m = 0; m < NT; ++m) {
+        const int g = w0 + m * 128 + q * 32 + lane;
+        const bool inside = g >= 0 && g < L;
+#pragma unroll
+        for (int cc = 0; cc < HC / 16; ++cc) {
+          const int col = hhalf * HC + cc * 16;
+          float v[16];
+          if (inside) {
+            const float4* src = reinterpret_cast<const float4*>(xg + (base + g) * C + col);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float4 t = src[e];
+              v[e * 4 + 0] = t.x + b0[col + e * 4 + 0];
+              v[e * 4 + 1] = t.y + b0[col + e * 4 + 1];
+              v[e * 4 + 2] = t.z + b0[col + e * 4 + 2];
+              v[e * 4 + 3] = t.w + b0[col + e * 4 + 3];
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) v[e] = 0.f;
+          }
+          tc::tmem_st16(lane_base + T0 + m * C + col, v);
+        }
+      }
+      tc::tmem_st_wait();
+    }
+    for (int d = 0; d < p.nd; ++d) {
+      const int dil = p.dil[j][d];
+      const uint8_t* inbuf = d == 0 ? bufX : bufY;
+      const int rows_in = d == 0 ? ROWSX : ROWSY;
+      const int halo_in = d == 0 ? p.HX : p.HY;
+      // ---- taps, in groups that fit the weight buffer --------------------------------------
+      for (int g0 = 0; g0 < k; g0 += p.wg) {
+        const int ntap = min(p.wg, k - g0);
+        {
+          const uint4* __restrict__ src = reinterpret_cast<const uint4*>(p.w16 + p.woff[j][d] + size_t(g0) * C * C);
+          const int n16 = ntap * C * C / 8;
+          for (int i = tid; i < n16; i += 256) reinterpret_cast<uint4*>(wbuf)[i] = src[i];
+        }
+        tc::fence_async_smem();  // bufX / bufY / wbuf writes -> async proxy
+        tc::fence_before_sync();
+        __syncthreads();
+        tc::fence_after_sync();
+        if (tid == 0) {
+          const uint32_t abase = tc::smem_u32(inbuf), wbase = tc::smem_u32(wbuf);
+#pragma unroll 1
+          for (int m = 0; m < NT; ++m) {
+#pragma unroll 1
+            for (int t = 0; t < ntap; ++t) {
+              const int arow = m * 128 + halo_in + (g0 + t - half) * dil;
+#pragma unroll
+              for (int ks = 0; ks < C / 16; ++ks) {
+                const uint64_t ad = tc::make_desc(abase + uint32_t((ks * 2) * rows_in + arow) * 16u, uint32_t(rows_in) * 16u, 128u);
+                const uint64_t bd = tc::make_desc(wbase + uint32_t((t * CH + ks * 2) * C) * 16u, uint32_t(C) * 16u, 128u);
+                tc::mma_f16_ss(tmem + T0 + m * C, ad, bd, idesc, 1u);
+              }
+            }
+          }
+          tc::mma_commit(&bar);
+        }
+        tc::mbar_wait(&bar, phase);
+        phase ^= 1u;
+        tc::fence_after_sync();
+      }
+      // ---- epilogue ---------------------------------------------------------------------------
+      if (d + 1 < p.nd) {
+        // y = T; bufY <- lrelu(y) (zero outside the utterance); T keeps y for the next conv
+#pragma unroll 1
+        for (int m = 0; m < NT; ++m) {
+          const int r = m * 128 + q * 32 + lane;
+          const int g = w0 + r;
+          const bool inside = g >= 0 && g < L;
+#pragma unroll
+          for (int cc = 0; cc < HC / 16; ++cc) {
+            const int col = hhalf * HC + cc * 16;
+            float v[16];
+            tc::tmem_ld16(lane_base + T0 + m * C + col, v);
+            tc::tmem_ld_wait();
+            uint32_t pk[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              float a = v[2 * e], b = v[2 * e + 1];
+              a = a >= 0.f ? a : 0.1f * a;
+              b = b >= 0.f ? b : 0.1f * b;
+              pk[e] = inside ? E::pack2(a, b) : 0u;
+            }
+            uint8_t* dst = bufY + (size_t(col / 8) * ROWSY + r + p.HY) * 16;
+            *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            *reinterpret_cast<uint4*>(dst + size_t(ROWSY) * 16) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          }
+        }
+      } else {
+        const bool first = j == 0, last = j == p.nk - 1;
+#pragma unroll 1
+        for (int m = 0; m < NT; ++m) {
+          const int r = m * 128 + q * 32 + lane;
+          const int g = w0 + r;
+          const bool store = r >= p.H && r < R - p.H && g < L;
+#pragma unroll
+          for (int cc = 0; cc < HC / 16; ++cc) {
+            const int col = hhalf * HC + cc * 16;
+            float v[16];
+            tc::tmem_ld16(lane_base + T0 + m * C + col, v);
+            if (!first) {
+              float s[16];
+              tc::tmem_ld16(lane_base + S0 + m * C + col, s);
+              tc::tmem_ld_wait();
+#pragma unroll
+              for (int e = 0; e < 16; ++e) v[e] += s[e];
+            } else {
+              tc::tmem_ld_wait();
+            }
+            if (!last) {
+              tc::tmem_st16(lane_base + S0 + m * C + col, v);
+            } else if (store) {
+              float4* dst = reinterpret_cast<float4*>(p.out + (base + g) * C + col);
+              const float* lb = p.late_bias;
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float4 o;
+                o.x = (v[e * 4 + 0] + lb[col + e * 4 + 0]) * p.inv_nk;
+                o.y = (v[e * 4 + 1] + lb[col + e * 4 + 1]) * p.inv_nk;
+                o.z = (v[e * 4 + 2] + lb[col + e * 4 + 2]) * p.inv_nk;
+                o.w = (v[e * 4 + 3] + lb[col + e * 4 + 3]) * p.inv_nk;
+                dst[e] = o;
+              }
+            }
+          }
+        }
+        if (!last) tc::tmem_st_wait();
+      }
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc<TCOLS>(tmem);
+}
+
+template <int C, int NT, int FMT>
+static void launch_mrf_inst(const MrfParams& p, int n_seg, int max_len, cudaStream_t st) {
+  const int R = NT * 128;
+  MrfParams q = p;
+  q.stride = R - 2 * p.H;
+  if (q.stride <= 0) throw std::runtime_error("mrf_tc: receptive field exceeds the window");
+  const size_t smem = size_t(C / 8) * 16 * (size_t(R + 2 * p.HX) + size_t(R + 2 * p.HY)) + size_t(p.wg) * C * C * 2;
+  auto kern = mrf_tc_kernel<C, NT, FMT>;
+  static thread_local size_t configured = 0;
+  if (configured < smem) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
+      throw std::runtime_error("mrf_tc: cannot reserve shared memory");
+    configured = smem;
+  }
+  const int L = max_len * p.scale;
+  dim3 grid((L + q.stride - 1) / q.stride, n_seg);
+  kern<<<grid, 256, smem, st>>>(q);
+  post_launch("mrf_tc_kernel", st);
+}
+
+bool mrf_tc_supported(int C, int nk, int nd, const int* k, int max_halo) {
+  if (!(C == 32 || C == 64 || C == 128)) return false;
+  if (nk < 1 || nk > 4 || nd < 1 || nd > 2) return false;
+  for (int j = 0; j < nk; ++j)
+    if (k[j] < 1 || k[j] > 11 || !(k[j] & 1)) return false;
+  return max_halo <= 60;
+}
+
+void launch_mrf_tc(const MrfParams& p, int C, int fmt, int n_seg, int max_len, cudaStream_t st) {
+  MrfParams q = p;
+  auto pick_wg = [&](int bytes_budget) {
+    int kmax = 1;
+    for (int j = 0; j < p.nk; ++j) kmax = max(kmax, p.k[j]);
+    return max(1, min(kmax, bytes_budget / (C * C * 2)));
+  };
+#define M3_MRF(CC, NT)                                                                    \
+  {                                                                                       \
+    if (fmt == 1) launch_mrf_inst<CC, NT, 1>(q, n_seg, max_len, st);                      \
+    else launch_mrf_inst<CC, NT, 0>(q, n_seg, max_len, st);                               \
+  }
+  if (C == 32) {
+    q.wg = pick_wg(16 * 1024);
+    M3_MRF(32, 4)
+  } else if (C == 64) {
+    q.wg = pick_wg(32 * 1024);
+    M3_MRF(64, 2)
+  } else if (C == 128) {
+    q.wg = pick_wg(64 * 1024);
+    M3_MRF(128, 2)
+  } else {
+    throw std::runtime_error("mrf_tc: unsupported channel count");
+  }
+#undef M3_MRF
+}
+
+}  // namespace m3

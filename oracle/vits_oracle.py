@@ -256,7 +256,7 @@ class VitsOracle:
         return z
 
     # ---- A.4 HiFi-GAN --------------------------------------------------------------
-    def decoder(self, z, g):
+    def decoder(self, z, g, taps=None):
         m = self.m
         x = self.conv(z, "dec.conv_pre", padding=3)
         if g is not None:
@@ -282,6 +282,8 @@ class VitsOracle:
                     y = y + t
                 xs = y if xs is None else xs + y
             x = xs / nk
+            if taps is not None:
+                taps[f"mrf{i}"] = x[0].t().numpy().copy()
         x = F.leaky_relu(x)  # slope 0.01
         x = F.conv1d(x, self.P["dec.conv_post.weight"], None, padding=3)
         return torch.tanh(x)
@@ -324,7 +326,7 @@ class VitsOracle:
             eps = torch.from_numpy(philox.normal(seed, 1, row, np.arange(Fr)[None, :], np.arange(self.I)[:, None]))[None]
             z_p = m_e + eps * torch.exp(logs_e) * float(noise_scale)
         z = self.flow(z_p, g)
-        o = self.decoder(z, g)
+        o = self.decoder(z, g, inter if return_intermediates else None)
         audio = o[0, 0].numpy()
         if return_intermediates:
             inter.update(x=x[0].t().numpy(), m_p=m_p[0].t().numpy(), logs_p=logs_p[0].t().numpy(),

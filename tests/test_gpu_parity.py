@@ -207,3 +207,36 @@ def test_b200voice_end_to_end(voices, built_library):
     b = v.ids_to_audio_batch([[4, 5, 6, 7, 8], [9, 10]], speakers=["p201", "p200"], noise_scale=0.0, noise_w=0.0)
     assert a.dtype == np.int16 and np.array_equal(a, b[0])
     assert int(np.abs(a.astype(np.int32)).max()) in (32766, 32767)
+
+
+def test_tensor_core_mrf_matches_oracle_and_simt(voices, built_library, oracles, monkeypatch):
+    """tcgen05 MRF (bf16 and fp16 operands, fp32 TMEM residual) vs the fp32 oracle, stage by stage,
+    and vs the fp32 SIMT path of the same library."""
+    from mimic3_b200.engine import B200Session
+    rng = np.random.default_rng(21)
+    orc = oracles("low_ms")
+    ids, lens = _batch(rng, 50, [37, 70, 3])
+    sid = np.array([5, 100, 42])
+    monkeypatch.setenv("M3B200_FORCE_SIMT", "1")
+    simt = B200Session(str(voices("low_ms")))
+    monkeypatch.delenv("M3B200_FORCE_SIMT")
+    ref = simt.infer(ids, lens, (0.0, 1.0, 0.0), sid, keep_float=True, debug_tensors=("mrf0", "mrf1", "mrf2"))
+    for fmt in ("bf16", "fp16"):
+        monkeypatch.setenv("M3B200_TC_FORMAT", fmt)
+        sess = B200Session(str(voices("low_ms")))
+        r = sess.infer(ids, lens, (0.0, 1.0, 0.0), sid, keep_float=True, debug_tensors=("mrf0", "mrf1", "mrf2"))
+        np.testing.assert_array_equal(r.frames, ref.frames)
+        for name in ("mrf0", "mrf1", "mrf2"):
+            a, b = r.tensors[name], ref.tensors[name]
+            rel = np.sqrt(np.mean((a - b) ** 2)) / np.sqrt(np.mean(b ** 2))
+            print(f"{fmt} {name}: relative RMS vs SIMT fp32 {rel:.3e}")
+            assert rel < (2e-2 if fmt == "bf16" else 3e-3), (fmt, name, rel)
+        off = 0
+        for b, L in enumerate(lens):
+            audio, inter = orc.infer(ids[b, :L], (0.0, 1.0, 0.0), sid=int(sid[b]), return_intermediates=True)
+            got = r.utterance_audio(b)
+            rms = float(np.sqrt(np.mean((got - audio) ** 2)))
+            print(f"{fmt} utt {b}: waveform RMS vs oracle {rms:.3e} (signal RMS {np.sqrt(np.mean(audio**2)):.3f})")
+            assert rms <= RMS_TOL, (fmt, b, rms)
+        sess.close()
+    simt.close()
