@@ -100,18 +100,80 @@ struct Builder {
   const HostVoice& hv;
   Packer pk;
   std::vector<Pending> fix;
+  std::vector<uint16_t> h16;  // tensor-core operands
+  int tc_fmt = 0;
   int64_t n_params = 0;
   explicit Builder(const HostVoice& h) : hv(h) {}
+
+  uint16_t cvt16(float f) const {
+    if (tc_fmt == 1) {
+      __nv_bfloat16 h = __float2bfloat16_rn(f);
+      return *reinterpret_cast<uint16_t*>(&h);
+    }
+    __half h = __float2half_rn(f);
+    return *reinterpret_cast<uint16_t*>(&h);
+  }
+
+  // Pack logical weights W[tap][k][n] (n < Ncols) for conv_tc_kernel.  gate: the Ncols = 2*N
+  // columns are (a | b) halves and every chunk carries NC/2 a-columns followed by their b-columns.
+  void tc_pack(TcConvW& t, const std::vector<float>& W, int taps, int K, int N, int dil, bool gate) {
+    t.ok = false;
+    const int ncols = gate ? 2 * N : N;
+    int best = 0;
+    long best_pad = -1;
+    for (int nc : {128, 96, 64, 32}) {
+      if (gate && nc % 64) continue;
+      if (!conv_tc_supported(K, nc, taps, dil)) continue;
+      const int per = gate ? nc / 2 : nc;
+      const long padded = long((N + per - 1) / per) * per;
+      if (best_pad < 0 || padded < best_pad) {
+        best_pad = padded;
+        best = nc;
+      }
+    }
+    if (!best) return;
+    const int NC = best, per = gate ? NC / 2 : NC;
+    const int chunks = (N + per - 1) / per;
+    while (h16.size() % 64) h16.push_back(0);
+    t.woff = h16.size();
+    const size_t o = h16.size();
+    h16.resize(o + size_t(chunks) * taps * K * NC, 0);
+    for (int c = 0; c < chunks; ++c)
+      for (int tap = 0; tap < taps; ++tap)
+        for (int k = 0; k < K; ++k)
+          for (int j = 0; j < NC; ++j) {
+            int col;
+            if (gate) {
+              const int ch = c * per + (j % per);
+              if (ch >= N) continue;
+              col = (j < per ? 0 : N) + ch;
+            } else {
+              col = c * NC + j;
+              if (col >= N) continue;
+            }
+            h16[o + ((size_t(c) * taps + tap) * (K / 8) + k / 8) * NC * 8 + size_t(j) * 8 + (k & 7)] =
+                cvt16(W[(size_t(tap) * K + k) * ncols + col]);
+          }
+    t.ok = true;
+    t.K = K;
+    t.NC = NC;
+    t.n_chunks = chunks;
+    t.N = N;
+    t.taps = taps;
+  }
 
   void place(const float** slot, const std::vector<float>& v) { fix.push_back({slot, pk.add(v)}); }
 
   // Conv1d weight (Cout, Cin, k) -> [k][Cin][Cout]
-  void conv(Lin& l, const std::string& base, int cout, int cin, int k, bool need_bias = true) {
+  // tc: 0 = fp32 SIMT only, 1 = also pack for the tensor-core conv, 2 = gated (cout = 2 * channels)
+  void conv(Lin& l, const std::string& base, int cout, int cin, int k, bool need_bias = true, int tc = 0) {
     const OnnxTensor& w = hv.need(base + ".weight", {cout, cin, k});
     std::vector<float> t(size_t(k) * cin * cout);
     for (int o = 0; o < cout; ++o)
       for (int i = 0; i < cin; ++i)
         for (int j = 0; j < k; ++j) t[(size_t(j) * cin + i) * cout + o] = w.f32[(size_t(o) * cin + i) * k + j];
+    if (tc && cin % 16 == 0 && (tc == 2 ? (cout / 2) % 16 == 0 : cout % 4 == 0))
+      tc_pack(l.tc, t, k, cin, tc == 2 ? cout / 2 : cout, 1, tc == 2);
     place(&l.w, t);
     n_params += int64_t(t.size());
     l.cin = cin;
@@ -162,6 +224,15 @@ std::unique_ptr<DeviceVoice> build_device_voice(const HostVoice& hv, int device)
   dv.device = device;
   const VoiceConfig& c = hv.cfg;
   Builder B(hv);
+  {
+    // tensor-core operand format: fp16 (default; 11-bit significand keeps the waveform within
+    // 1e-4 RMS of fp32) or bf16 (M3B200_TC_FORMAT=bf16).  Accumulation is always fp32.
+    const char* fe = getenv("M3B200_TC_FORMAT");
+    dv.tc_fmt = (fe && std::string(fe) == "bf16") ? 1 : 0;
+    B.tc_fmt = dv.tc_fmt;
+    const char* fs = getenv("M3B200_FORCE_SIMT");
+    dv.use_tc = !(fs && *fs && *fs != '0');
+  }
   const int H = c.hidden, I = c.inter, Ff = c.filter;
   const int dk = H / c.n_heads;
 
@@ -312,13 +383,13 @@ std::unique_ptr<DeviceVoice> build_device_voice(const HostVoice& hv, int device)
     for (int f = nflows - 1; f >= 0; --f) {
       const std::string p = "flow.flows." + std::to_string(2 * f);
       CouplingW& cw = dv.couplings[idx++];
-      B.conv(cw.pre, p + ".pre", Hf, I / 2, 1);
-      B.conv(cw.post, p + ".post", I / 2, Hf, 1);
+      B.conv(cw.pre, p + ".pre", Hf, I / 2, 1, true, 1);
+      B.conv(cw.post, p + ".post", I / 2, Hf, 1, true, 1);
       cw.in.resize(nl);
       cw.rs.resize(nl);
       for (int i = 0; i < nl; ++i) {
-        B.conv(cw.in[i], p + ".enc.in_layers." + std::to_string(i), 2 * Hf, Hf, dv.flow_kernel);
-        B.conv(cw.rs[i], p + ".enc.res_skip_layers." + std::to_string(i), i < nl - 1 ? 2 * Hf : Hf, Hf, 1);
+        B.conv(cw.in[i], p + ".enc.in_layers." + std::to_string(i), 2 * Hf, Hf, dv.flow_kernel, true, 2);
+        B.conv(cw.rs[i], p + ".enc.res_skip_layers." + std::to_string(i), i < nl - 1 ? 2 * Hf : Hf, Hf, 1, true, 1);
       }
       cw.cond_off = add_cond(p + ".enc.cond_layer", 2 * Hf * nl);
     }
@@ -327,7 +398,7 @@ std::unique_ptr<DeviceVoice> build_device_voice(const HostVoice& hv, int device)
   // ---- HiFi-GAN decoder
   {
     const int C0 = c.up_init;
-    B.conv(dv.dec_pre, "dec.conv_pre", C0, I, 7);
+    B.conv(dv.dec_pre, "dec.conv_pre", C0, I, 7, true, 1);
     dv.dec_cond_off = add_cond("dec.cond", C0);
     const int nk = int(c.rb_kernels.size());
     dv.ups.resize(c.up_rates.size());
@@ -352,6 +423,17 @@ std::unique_ptr<DeviceVoice> build_device_voice(const HostVoice& hv, int device)
             for (int co = 0; co < u.cout; ++co)
               t[((size_t(j1) * u.ntaps + mp) * u.cin + ci) * u.cout + co] = w.f32[(size_t(ci) * u.cout + co) * u.k + j];
         }
+      if (u.cin % 16 == 0 && u.cout % 4 == 0) {
+        // logical [tap m'][ci][phase*Cout + co] for the polyphase GEMM (N = u * Cout)
+        std::vector<float> lw(size_t(u.ntaps) * u.cin * u.u * u.cout, 0.f);
+        for (int j1 = 0; j1 < u.u; ++j1)
+          for (int mp = 0; mp < u.ntaps; ++mp)
+            for (int ci = 0; ci < u.cin; ++ci)
+              for (int co = 0; co < u.cout; ++co)
+                lw[(size_t(mp) * u.cin + ci) * (u.u * u.cout) + j1 * u.cout + co] =
+                    t[((size_t(j1) * u.ntaps + mp) * u.cin + ci) * u.cout + co];
+        B.tc_pack(u.tc, lw, u.ntaps, u.cin, u.u * u.cout, 1, false);
+      }
       B.place(&u.w, t);
       B.n_params += w.numel();
       B.vec(&u.b, "dec.ups." + std::to_string(i) + ".bias", u.cout);
@@ -388,20 +470,9 @@ std::unique_ptr<DeviceVoice> build_device_voice(const HostVoice& hv, int device)
   }
 
   // ---- tensor-core operands of the MRF stages: per conv [tap][Cin/8][Cout][8], 16-bit
-  std::vector<uint16_t> h16;
+  std::vector<uint16_t>& h16 = B.h16;
   {
-    const char* fe = getenv("M3B200_TC_FORMAT");
-    dv.tc_fmt = (fe && std::string(fe) == "fp16") ? 0 : 1;
-    const char* fs = getenv("M3B200_FORCE_SIMT");
-    dv.use_tc = !(fs && *fs && *fs != '0');
-    auto cvt = [&](float f) -> uint16_t {
-      if (dv.tc_fmt == 1) {
-        __nv_bfloat16 h = __float2bfloat16_rn(f);
-        return *reinterpret_cast<uint16_t*>(&h);
-      }
-      __half h = __float2half_rn(f);
-      return *reinterpret_cast<uint16_t*>(&h);
-    };
+    auto cvt = [&](float f) -> uint16_t { return B.cvt16(f); };
     const int nk = int(c.rb_kernels.size());
     dv.mrf.resize(c.up_rates.size());
     for (size_t i = 0; i < c.up_rates.size(); ++i) {
@@ -567,6 +638,30 @@ struct Run {
     return p;
   }
   void conv(const ConvParams& p, const Segs& s) const { launch_conv(p, s.n, s.max_len, st); }
+
+  bool tc_ok(const TcConvW& t) const { return dv.use_tc && t.ok; }
+  TcConvParams base_tc(const TcConvW& t, const float* bias, const float* in, int in_stride, float* out,
+                       int out_stride, const Segs& s, int scale) const {
+    TcConvParams p;
+    p.in = in;
+    p.in_stride = in_stride;
+    p.K = t.K;
+    p.w = dv.slab16 + t.woff;
+    p.NC = t.NC;
+    p.n_chunks = t.n_chunks;
+    p.N = t.N;
+    p.taps = t.taps;
+    p.pad_left = (t.taps - 1) / 2;
+    p.bias = bias;
+    p.out = out;
+    p.out_stride = out_stride;
+    p.seg_off = s.off;
+    p.seg_len = s.len;
+    p.in_scale = scale;
+    p.out_scale = scale;
+    return p;
+  }
+  void tc_conv(const TcConvParams& p, const Segs& s) const { launch_conv_tc(p, dv.tc_fmt, s.n, s.max_len, st); }
 
   void dump(const char* name, const float* d, int64_t rows, int64_t cols) const {
     if (!debug) return;
@@ -868,11 +963,20 @@ Result* run_inference(Voice& v, const int64_t* ids, const int64_t* lengths, int 
     for (size_t f = 0; f < dv.couplings.size(); ++f) {
       const CouplingW& cw = dv.couplings[f];
       launch_flip_channels(z, int(NF), I, st);
-      R.conv(R.base_conv(cw.pre, z, I, h, Hf, frm, 1), frm);  // x0 = z[:, :half]
+      if (R.tc_ok(cw.pre.tc)) R.tc_conv(R.base_tc(cw.pre.tc, cw.pre.b, z, I, h, Hf, frm, 1), frm);
+      else R.conv(R.base_conv(cw.pre, z, I, h, Hf, frm, 1), frm);  // x0 = z[:, :half]
       M3_CUDA(cudaMemsetAsync(skip, 0, size_t(NF) * Hf * 4, st));
       const int nl = dv.flow_layers;
       for (int i = 0; i < nl; ++i) {
-        {
+        if (R.tc_ok(cw.in[i].tc)) {
+          TcConvParams p = R.base_tc(cw.in[i].tc, cw.in[i].b, h, Hf, act, Hf, frm, 1);
+          p.epi = TC_GATE;
+          if (const float* ub = ubias(cw.cond_off)) {
+            p.ubias = ub + size_t(i) * 2 * Hf;
+            p.ub_stride = dv.n_cond;
+          }
+          R.tc_conv(p, frm);
+        } else {
           ConvParams p = R.base_conv(cw.in[i], h, Hf, act, Hf, frm, 1);
           p.Cout = Hf;
           p.gate = 1;
@@ -882,7 +986,19 @@ Result* run_inference(Voice& v, const int64_t* ids, const int64_t* lengths, int 
           }
           R.conv(p, frm);
         }
-        {
+        if (R.tc_ok(cw.rs[i].tc)) {
+          TcConvParams p = R.base_tc(cw.rs[i].tc, cw.rs[i].b, act, Hf, h, Hf, frm, 1);
+          p.epi = TC_RES_SKIP;
+          if (i < nl - 1) {
+            p.split = Hf;
+            p.out2 = skip;
+            p.out2_stride = Hf;
+          } else {
+            p.out = skip;
+            p.out_stride = Hf;
+          }
+          R.tc_conv(p, frm);
+        } else {
           ConvParams p = R.base_conv(cw.rs[i], act, Hf, h, Hf, frm, 1);
           p.mode = 1;
           if (i < nl - 1) {
@@ -896,7 +1012,12 @@ Result* run_inference(Voice& v, const int64_t* ids, const int64_t* lengths, int 
           R.conv(p, frm);
         }
       }
-      {
+      if (R.tc_ok(cw.post.tc)) {
+        TcConvParams p = R.base_tc(cw.post.tc, cw.post.b, skip, Hf, z, I, frm, 1);
+        p.out_coff = half;
+        p.epi = TC_SUB;  // x1 = x1 - m   (mean_only coupling)
+        R.tc_conv(p, frm);
+      } else {
         ConvParams p = R.base_conv(cw.post, skip, Hf, z, I, frm, 1);
         p.out_coff = half;
         p.mode = 2;  // x1 = x1 - m   (mean_only coupling)
@@ -909,7 +1030,14 @@ Result* run_inference(Voice& v, const int64_t* ids, const int64_t* lengths, int 
 
   // ---------------- A.4 HiFi-GAN ----------------
   float* cur = A2.alloc<float>(size_t(NF) * C0);
-  {
+  if (R.tc_ok(dv.dec_pre.tc)) {
+    TcConvParams p = R.base_tc(dv.dec_pre.tc, dv.dec_pre.b, z, I, cur, C0, frm, 1);
+    if (const float* ub = ubias(dv.dec_cond_off)) {
+      p.ubias = ub;
+      p.ub_stride = dv.n_cond;
+    }
+    R.tc_conv(p, frm);
+  } else {
     ConvParams p = R.base_conv(dv.dec_pre, z, I, cur, C0, frm, 1);
     if (const float* ub = ubias(dv.dec_cond_off)) {
       p.ubias = ub;
@@ -928,7 +1056,19 @@ Result* run_inference(Voice& v, const int64_t* ids, const int64_t* lengths, int 
     float* yb[2] = {A2.alloc<float>(n), A2.alloc<float>(n)};
     float* tb = A2.alloc<float>(n);
     float* sum = A2.alloc<float>(n);
-    {
+    if (R.tc_ok(u.tc)) {
+      Segs fs{d_frm_off, d_frm_len, batch, Fmax};
+      TcConvParams p = R.base_tc(u.tc, u.b, cur, u.cin, xu, u.cout, fs, scale);
+      p.in_slope = 0.1f;
+      p.pad_left = u.ntaps - 1;
+      p.epi = TC_UPS;
+      p.out_scale = out_scale;
+      p.rows_extra = u.ntaps - 1;
+      p.ups_u = u.u;
+      p.ups_pad = u.pad;
+      p.ups_cout = u.cout;
+      launch_conv_tc(p, dv.tc_fmt, batch, Fmax, st);
+    } else {
       ConvParams p;
       p.in = cur;
       p.in_stride = u.cin;

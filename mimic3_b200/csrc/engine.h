@@ -26,10 +26,17 @@ struct EngineError : std::runtime_error {
       throw ::m3::EngineError(4, std::string("CUDA error: ") + cudaGetErrorString(_e) + " at " #expr); \
   } while (0)
 
+struct TcConvW {  // 16-bit tensor-core packing [chunk][tap][K/8][NC][8] (kernels_tc_conv.cu)
+  bool ok = false;
+  unsigned long long woff = 0;  // element offset into DeviceVoice::slab16
+  int K = 0, NC = 0, n_chunks = 0, N = 0, taps = 1;
+};
+
 struct Lin {  // a Conv1d packed as [taps][Cin][ldw] (+ bias[ldw])
   const float* w = nullptr;
   const float* b = nullptr;
   int cin = 0, cout = 0, taps = 1;
+  TcConvW tc;
 };
 
 struct DDSW {
@@ -60,6 +67,7 @@ struct UpW {
   const float* w = nullptr;  // [phase u][ntaps][Cin][Cout]
   const float* b = nullptr;
   int cin = 0, cout = 0, k = 0, u = 0, ntaps = 0, pad = 0;
+  TcConvW tc;
 };
 
 struct ResBlockW {

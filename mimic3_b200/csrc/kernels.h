@@ -65,6 +65,32 @@ struct MrfParams {
   int wg = 1;      // taps per weight-staging group (launcher)
   float inv_nk = 1.f;
 };
+// Generic tensor-core Conv1d / polyphase ConvTranspose1d (kernels_tc.cu).
+// Weights: 16-bit, [chunk][tap][K/8][NC][8] (one contiguous block per (chunk, tap): a bulk copy).
+enum TcEpi { TC_STORE = 0, TC_GATE = 1, TC_RES_SKIP = 2, TC_SUB = 3, TC_UPS = 4 };
+struct TcConvParams {
+  const float* in = nullptr;
+  int in_stride = 0, in_coff = 0, K = 0;
+  float in_slope = 1.f;
+  const uint16_t* w = nullptr;
+  int NC = 0, n_chunks = 0, N = 0;  // N = logical output columns (gate: gated channels)
+  int taps = 1, dil = 1, pad_left = 0;
+  int epi = TC_STORE;
+  const float* bias = nullptr;
+  const float* ubias = nullptr;
+  int ub_stride = 0;
+  float* out = nullptr;
+  int out_stride = 0, out_coff = 0;
+  float* out2 = nullptr;
+  int out2_stride = 0, split = 1 << 30;
+  const int* seg_off = nullptr;
+  const int* seg_len = nullptr;
+  int in_scale = 1, out_scale = 1, rows_extra = 0;
+  int ups_u = 1, ups_pad = 0, ups_cout = 0;
+};
+bool conv_tc_supported(int K, int NC, int taps, int dil);
+void launch_conv_tc(const TcConvParams& p, int fmt, int n_seg, int max_seg_len, cudaStream_t st);
+
 bool mrf_tc_supported(int C, int nk, int nd, const int* k, int max_halo);
 // fmt: 0 = fp16 operands, 1 = bf16 operands
 void launch_mrf_tc(const MrfParams& p, int C, int fmt, int n_seg, int max_len, cudaStream_t st);

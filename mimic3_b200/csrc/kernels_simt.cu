@@ -814,26 +814,47 @@ void launch_flip_channels(float* x, int rows, int C, cudaStream_t st) {
 // -------------------------------------------------------------------------------------
 // conv_post (C -> 1, no bias) + tanh + per-utterance peak; int16 conversion
 // -------------------------------------------------------------------------------------
+// One CTA: 256 consecutive samples.  The (256 + k - 1) x C input tile is staged in smem with
+// coalesced float4 loads (lrelu applied on the way in); rows are padded to C+1 floats so the
+// per-thread row walk is bank-conflict free.
 __global__ void __launch_bounds__(256) conv_post_kernel(const float* __restrict__ x, int C,
                                                         const float* __restrict__ w, int k, float slope,
                                                         float* audio, unsigned* peak_bits, const int* seg_off,
                                                         const int* seg_len, int scale) {
-  extern __shared__ float ws[];
-  for (int i = threadIdx.x; i < k * C; i += 256) ws[i] = w[i];
-  __syncthreads();
+  extern __shared__ float sm[];
   const int seg = blockIdx.y;
   const int L = seg_len[seg] * scale;
+  const int t0 = blockIdx.x * 256;
+  if (t0 >= L) return;
   const long long base = (long long)seg_off[seg] * scale;
-  const int t = blockIdx.x * 256 + threadIdx.x;
+  const int pad = (k - 1) / 2;
+  const int rows = 256 + k - 1;
+  const int ld = C + 1;
+  float* ws = sm;             // [k][C]
+  float* tile = sm + k * C;   // [rows][C+1]
+  for (int i = threadIdx.x; i < k * C; i += 256) ws[i] = w[i];
+  const int c4n = C / 4;
+  for (int i = threadIdx.x; i < rows * c4n; i += 256) {
+    const int r = i / c4n, c4 = i - r * c4n;
+    const int ti = t0 + r - pad;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ti >= 0 && ti < L) v = *reinterpret_cast<const float4*>(x + (base + ti) * C + c4 * 4);
+    float* d = tile + r * ld + c4 * 4;
+    d[0] = lrelu(v.x, slope);
+    d[1] = lrelu(v.y, slope);
+    d[2] = lrelu(v.z, slope);
+    d[3] = lrelu(v.w, slope);
+  }
+  __syncthreads();
+  const int t = t0 + threadIdx.x;
   float y = 0.f;
   if (t < L) {
     float s = 0.f;
-    const int pad = (k - 1) / 2;
     for (int j = 0; j < k; ++j) {
-      const int ti = t + j - pad;
-      if (ti < 0 || ti >= L) continue;
-      const float* row = x + (base + ti) * C;
-      for (int c = 0; c < C; ++c) s = fmaf(ws[j * C + c], lrelu(row[c], slope), s);
+      const float* row = tile + (threadIdx.x + j) * ld;
+      const float* wj = ws + j * C;
+#pragma unroll 8
+      for (int c = 0; c < C; ++c) s = fmaf(wj[c], row[c], s);
     }
     y = tanhf(s);
     audio[base + t] = y;
@@ -851,8 +872,15 @@ __global__ void __launch_bounds__(256) conv_post_kernel(const float* __restrict_
 void launch_conv_post(const float* x, int C, const float* w, int k, float slope, float* audio, unsigned* peak_bits,
                       const int* seg_off, const int* seg_len, int scale, int n_seg, int max_len, cudaStream_t st) {
   if (max_len <= 0) return;
-  conv_post_kernel<<<dim3((max_len * scale + 255) / 256, n_seg), 256, sizeof(float) * k * C, st>>>(
-      x, C, w, k, slope, audio, peak_bits, seg_off, seg_len, scale);
+  if (C % 4) throw std::runtime_error("conv_post: channel count must be a multiple of 4");
+  const size_t smem = sizeof(float) * (size_t(k) * C + size_t(256 + k - 1) * (C + 1));
+  static thread_local size_t configured = 0;
+  if (smem > 48 * 1024 && configured < smem) {
+    cudaFuncSetAttribute(conv_post_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    configured = smem;
+  }
+  conv_post_kernel<<<dim3((max_len * scale + 255) / 256, n_seg), 256, smem, st>>>(x, C, w, k, slope, audio,
+                                                                                  peak_bits, seg_off, seg_len, scale);
   M3_LAUNCHED();
 }
 
