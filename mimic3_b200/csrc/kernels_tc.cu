@@ -23,11 +23,24 @@ namespace m3 {
 // therefore advance by R - 2H.  Rows outside the utterance are zeroed in bufX/bufY, which
 // reproduces the reference's per-layer zero padding (batch-1 edge semantics).
 // =====================================================================================
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(tc::smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+// v2 pipeline inside the CTA:
+//   * x of the window is read from global exactly twice (once as the 16-bit A operand, once into
+//     registers for the three T <- x + b initialisations);
+//   * conv weights stream through a 2-deep cp.async ring, one tap-group ahead of the MMAs;
+//   * the last tap-group of every conv commits one mbarrier per 128-row tile, so the epilogue of
+//     tile m runs while the tensor pipe is still working on tiles m+1.. .
 template <int C, int NT, int FMT>
 __global__ void __launch_bounds__(256, (C == 32 || (C == 64 && NT <= 2)) ? 2 : 1) mrf_tc_kernel(MrfParams p) {
   constexpr int R = NT * 128;
   constexpr int CH = C / 8;        // 16-byte K-chunks per row
   constexpr int HC = C / 2;        // columns per epilogue thread (two column halves)
+  constexpr int NCC = HC / 16;     // 16-column groups per thread
   constexpr int TCOLS_RAW = 2 * NT * C;
   constexpr int TCOLS = TCOLS_RAW <= 32 ? 32 : TCOLS_RAW <= 64 ? 64 : TCOLS_RAW <= 128 ? 128 : TCOLS_RAW <= 256 ? 256 : 512;
   static_assert(TCOLS_RAW <= 512, "TMEM budget");
@@ -35,7 +48,7 @@ __global__ void __launch_bounds__(256, (C == 32 || (C == 64 && NT <= 2)) ? 2 : 1
 
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint32_t tmem_slot;
-  __shared__ __align__(8) uint64_t bar;
+  __shared__ __align__(8) uint64_t gbar, tbar[NT];
 
   const int seg = blockIdx.y;
   const int L = p.seg_len[seg] * p.scale;
@@ -44,20 +57,54 @@ __global__ void __launch_bounds__(256, (C == 32 || (C == 64 && NT <= 2)) ? 2 : 1
   const long long base = (long long)p.seg_off[seg] * p.scale;
   const int w0 = o0 - p.H;
   const int ROWSX = R + 2 * p.HX, ROWSY = R + 2 * p.HY;
+  const uint32_t wb_bytes = uint32_t(p.wg) * C * C * 2;
   uint8_t* bufX = smem;
   uint8_t* bufY = bufX + size_t(CH) * ROWSX * 16;
-  uint8_t* wbuf = bufY + size_t(CH) * ROWSY * 16;
+  uint8_t* wbuf = bufY + size_t(CH) * ROWSY * 16;  // two buffers of wb_bytes
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q = warp & 3, hhalf = warp >> 2;
   const float* __restrict__ xg = p.x;
 
+  // weight tap-groups in kernel order: (resblock j, conv d, first tap g0)
+  auto group_src = [&](int j, int d, int g0) { return p.w16 + p.woff[j][d] + size_t(g0) * C * C; };
+  auto prefetch = [&](int j, int d, int g0, int buf) {
+    const int ntap = min(p.wg, p.k[j] - g0);
+    const uint4* __restrict__ src = reinterpret_cast<const uint4*>(group_src(j, d, g0));
+    uint4* dst = reinterpret_cast<uint4*>(wbuf + size_t(buf) * wb_bytes);
+    const int n16 = ntap * C * C / 8;
+    for (int i = tid; i < n16; i += 256) cp_async16(dst + i, src + i);
+    cp_async_commit();
+  };
+  prefetch(0, 0, 0, 0);
+
   if (warp == 0) tc::tmem_alloc<TCOLS>(&tmem_slot);
   if (tid == 0) {
-    tc::mbar_init(&bar, 1);
+    tc::mbar_init(&gbar, 1);
+    for (int m = 0; m < NT; ++m) tc::mbar_init(&tbar[m], 1);
     tc::mbar_fence_init();
   }
-  // ---- stage lrelu(x) of the window (+halo) as the A operand -------------------------
+  // ---- x window -> registers (fp32, for the residual stream) ---------------------------------
+  float xr[NT][NCC][16];
+#pragma unroll
+  for (int m = 0; m < NT; ++m) {
+    const int g = w0 + m * 128 + q * 32 + lane;
+    const bool inside = g >= 0 && g < L;
+#pragma unroll
+    for (int cc = 0; cc < NCC; ++cc) {
+      const int col = hhalf * HC + cc * 16;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (inside) t = *reinterpret_cast<const float4*>(xg + (base + g) * C + col + e * 4);
+        xr[m][cc][e * 4 + 0] = t.x;
+        xr[m][cc][e * 4 + 1] = t.y;
+        xr[m][cc][e * 4 + 2] = t.z;
+        xr[m][cc][e * 4 + 3] = t.w;
+      }
+    }
+  }
+  // ---- lrelu(x) of the window (+halo) as the 16-bit A operand ----------------------------------
   for (int idx = tid; idx < CH * ROWSX; idx += 256) {
     const int c8 = idx / ROWSX, rr = idx - c8 * ROWSX;
     const int g = w0 - p.HX + rr;
@@ -80,36 +127,24 @@ __global__ void __launch_bounds__(256, (C == 32 || (C == 64 && NT <= 2)) ? 2 : 1
   const uint32_t lane_base = tmem + (uint32_t(q * 32) << 16);
   const uint32_t T0 = 0, S0 = NT * C;  // column offsets of the two TMEM regions
   const uint32_t idesc = tc::make_idesc(128, C, FMT);
-  uint32_t phase = 0;
+  uint32_t gphase = 0, tphase = 0;
+  int gi = 0;                 // running tap-group index (selects the weight buffer)
+  bool prev_nonlast = false;  // previous group committed to gbar and has not been awaited yet
 
   for (int j = 0; j < p.nk; ++j) {
     const int k = p.k[j];
     const int half = (k - 1) / 2;
-    // ---- T <- x + bias of the first conv -------------------------------------------------
+    // ---- T <- x + bias of the first conv (registers -> TMEM) -----------------------------------
     {
       const float* __restrict__ b0 = p.bias[j][0];
-#pragma unroll 1
-      for (int m = 0; m < NT; ++m) {
-        const int g = w0 + m * 128 + q * 32 + lane;
-        const bool inside = g >= 0 && g < L;
 #pragma unroll
-        for (int cc = 0; cc < HC / 16; ++cc) {
+      for (int m = 0; m < NT; ++m) {
+#pragma unroll
+        for (int cc = 0; cc < NCC; ++cc) {
           const int col = hhalf * HC + cc * 16;
           float v[16];
-          if (inside) {
-            const float4* src = reinterpret_cast<const float4*>(xg + (base + g) * C + col);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float4 t = src[e];
-              v[e * 4 + 0] = t.x + b0[col + e * 4 + 0];
-              v[e * 4 + 1] = t.y + b0[col + e * 4 + 1];
-              v[e * 4 + 2] = t.z + b0[col + e * 4 + 2];
-              v[e * 4 + 3] = t.w + b0[col + e * 4 + 3];
-            }
-          } else {
-#pragma unroll
-            for (int e = 0; e < 16; ++e) v[e] = 0.f;
-          }
+          for (int e = 0; e < 16; ++e) v[e] = xr[m][cc][e] + b0[col + e];
           tc::tmem_st16(lane_base + T0 + m * C + col, v);
         }
       }
@@ -120,20 +155,16 @@ __global__ void __launch_bounds__(256, (C == 32 || (C == 64 && NT <= 2)) ? 2 : 1
       const uint8_t* inbuf = d == 0 ? bufX : bufY;
       const int rows_in = d == 0 ? ROWSX : ROWSY;
       const int halo_in = d == 0 ? p.HX : p.HY;
-      // ---- taps, in groups that fit the weight buffer --------------------------------------
-      for (int g0 = 0; g0 < k; g0 += p.wg) {
+      for (int g0 = 0; g0 < k; g0 += p.wg, ++gi) {
         const int ntap = min(p.wg, k - g0);
-        {
-          const uint4* __restrict__ src = reinterpret_cast<const uint4*>(p.w16 + p.woff[j][d] + size_t(g0) * C * C);
-          const int n16 = ntap * C * C / 8;
-          for (int i = tid; i < n16; i += 256) reinterpret_cast<uint4*>(wbuf)[i] = src[i];
-        }
-        tc::fence_async_smem();  // bufX / bufY / wbuf writes -> async proxy
+        const bool last_group = g0 + p.wg >= k;
+        cp_async_wait_all();
+        tc::fence_async_smem();  // bufX / bufY / weight ring writes -> async proxy
         tc::fence_before_sync();
         __syncthreads();
         tc::fence_after_sync();
         if (tid == 0) {
-          const uint32_t abase = tc::smem_u32(inbuf), wbase = tc::smem_u32(wbuf);
+          const uint32_t abase = tc::smem_u32(inbuf), wbase = tc::smem_u32(wbuf + size_t(gi & 1) * wb_bytes);
 #pragma unroll 1
           for (int m = 0; m < NT; ++m) {
 #pragma unroll 1
@@ -146,23 +177,39 @@ __global__ void __launch_bounds__(256, (C == 32 || (C == 64 && NT <= 2)) ? 2 : 1
                 tc::mma_f16_ss(tmem + T0 + m * C, ad, bd, idesc, 1u);
               }
             }
+            if (last_group) tc::mma_commit(&tbar[m]);
           }
-          tc::mma_commit(&bar);
+          if (!last_group) tc::mma_commit(&gbar);
         }
-        tc::mbar_wait(&bar, phase);
-        phase ^= 1u;
-        tc::fence_after_sync();
+        // the buffer the NEXT group will land in was last read by the PREVIOUS group
+        if (prev_nonlast) {
+          tc::mbar_wait(&gbar, gphase);
+          gphase ^= 1u;
+        }
+        prev_nonlast = !last_group;
+        {  // prefetch the next tap-group of the whole kernel into the other buffer
+          int nj = j, nd2 = d, ng = g0 + p.wg;
+          if (ng >= k) {
+            ng = 0;
+            if (++nd2 >= p.nd) {
+              nd2 = 0;
+              ++nj;
+            }
+          }
+          if (nj < p.nk) prefetch(nj, nd2, ng, (gi + 1) & 1);
+        }
       }
-      // ---- epilogue ---------------------------------------------------------------------------
+      // ---- epilogue, tile by tile as the per-tile barriers fire -----------------------------------
       if (d + 1 < p.nd) {
-        // y = T; bufY <- lrelu(y) (zero outside the utterance); T keeps y for the next conv
 #pragma unroll 1
         for (int m = 0; m < NT; ++m) {
+          tc::mbar_wait(&tbar[m], tphase);
+          tc::fence_after_sync();
           const int r = m * 128 + q * 32 + lane;
           const int g = w0 + r;
           const bool inside = g >= 0 && g < L;
 #pragma unroll
-          for (int cc = 0; cc < HC / 16; ++cc) {
+          for (int cc = 0; cc < NCC; ++cc) {
             const int col = hhalf * HC + cc * 16;
             float v[16];
             tc::tmem_ld16(lane_base + T0 + m * C + col, v);
@@ -184,11 +231,13 @@ __global__ void __launch_bounds__(256, (C == 32 || (C == 64 && NT <= 2)) ? 2 : 1
         const bool first = j == 0, last = j == p.nk - 1;
 #pragma unroll 1
         for (int m = 0; m < NT; ++m) {
+          tc::mbar_wait(&tbar[m], tphase);
+          tc::fence_after_sync();
           const int r = m * 128 + q * 32 + lane;
           const int g = w0 + r;
           const bool store = r >= p.H && r < R - p.H && g < L;
 #pragma unroll
-          for (int cc = 0; cc < HC / 16; ++cc) {
+          for (int cc = 0; cc < NCC; ++cc) {
             const int col = hhalf * HC + cc * 16;
             float v[16];
             tc::tmem_ld16(lane_base + T0 + m * C + col, v);
@@ -220,6 +269,7 @@ __global__ void __launch_bounds__(256, (C == 32 || (C == 64 && NT <= 2)) ? 2 : 1
         }
         if (!last) tc::tmem_st_wait();
       }
+      tphase ^= 1u;
     }
   }
   tc::fence_before_sync();
@@ -233,7 +283,7 @@ static void launch_mrf_inst(const MrfParams& p, int n_seg, int max_len, cudaStre
   MrfParams q = p;
   q.stride = R - 2 * p.H;
   if (q.stride <= 0) throw std::runtime_error("mrf_tc: receptive field exceeds the window");
-  const size_t smem = size_t(C / 8) * 16 * (size_t(R + 2 * p.HX) + size_t(R + 2 * p.HY)) + size_t(p.wg) * C * C * 2;
+  const size_t smem = size_t(C / 8) * 16 * (size_t(R + 2 * p.HX) + size_t(R + 2 * p.HY)) + size_t(2) * p.wg * C * C * 2;
   auto kern = mrf_tc_kernel<C, NT, FMT>;
   static thread_local size_t configured = 0;
   if (configured < smem) {
@@ -268,13 +318,13 @@ void launch_mrf_tc(const MrfParams& p, int C, int fmt, int n_seg, int max_len, c
     else launch_mrf_inst<CC, NT, 0>(q, n_seg, max_len, st);                               \
   }
   if (C == 32) {
-    q.wg = pick_wg(16 * 1024);
+    q.wg = pick_wg(16 * 1024);  // whole conv (<= 14 KB) per buffer; ~100 KB/CTA -> 2 CTAs/SM
     M3_MRF(32, 4)
   } else if (C == 64) {
-    q.wg = pick_wg(32 * 1024);
+    q.wg = pick_wg(16 * 1024);  // 2 taps per buffer; ~109 KB/CTA -> 2 CTAs/SM
     M3_MRF(64, 2)
   } else if (C == 128) {
-    q.wg = pick_wg(64 * 1024);
+    q.wg = pick_wg(32 * 1024);  // 1 tap per buffer
     M3_MRF(128, 2)
   } else {
     throw std::runtime_error("mrf_tc: unsupported channel count");
