@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(256, (C == 32 || (C == 64 && NT <= 2)) ? 2 : 1
 
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint32_t tmem_slot;
-  __shared__ __align__(8) uint64_t gbar, tbar[NT];
+  __shared__ __align__(8) uint64_t gbar[2], tbar[NT];
 
   const int seg = blockIdx.y;
   const int L = p.seg_len[seg] * p.scale;
@@ -80,7 +80,8 @@ __global__ void __launch_bounds__(256, (C == 32 || (C == 64 && NT <= 2)) ? 2 : 1
 
   if (warp == 0) tc::tmem_alloc<TCOLS>(&tmem_slot);
   if (tid == 0) {
-    tc::mbar_init(&gbar, 1);
+    tc::mbar_init(&gbar[0], 1);
+    tc::mbar_init(&gbar[1], 1);
     for (int m = 0; m < NT; ++m) tc::mbar_init(&tbar[m], 1);
     tc::mbar_fence_init();
   }
@@ -127,7 +128,7 @@ __global__ void __launch_bounds__(256, (C == 32 || (C == 64 && NT <= 2)) ? 2 : 1
   const uint32_t lane_base = tmem + (uint32_t(q * 32) << 16);
   const uint32_t T0 = 0, S0 = NT * C;  // column offsets of the two TMEM regions
   const uint32_t idesc = tc::make_idesc(128, C, FMT);
-  uint32_t gphase = 0, tphase = 0;
+  uint32_t gphase[2] = {0u, 0u}, tphase = 0;  // gbar[b] guards weight buffer b (one pending arrival max)
   int gi = 0;                 // running tap-group index (selects the weight buffer)
   bool prev_nonlast = false;  // previous group committed to gbar and has not been awaited yet
 
@@ -179,12 +180,13 @@ __global__ void __launch_bounds__(256, (C == 32 || (C == 64 && NT <= 2)) ? 2 : 1
             }
             if (last_group) tc::mma_commit(&tbar[m]);
           }
-          if (!last_group) tc::mma_commit(&gbar);
+          if (!last_group) tc::mma_commit(&gbar[gi & 1]);
         }
         // the buffer the NEXT group will land in was last read by the PREVIOUS group
         if (prev_nonlast) {
-          tc::mbar_wait(&gbar, gphase);
-          gphase ^= 1u;
+          const int pb = (gi - 1) & 1;
+          tc::mbar_wait(&gbar[pb], gphase[pb]);
+          gphase[pb] ^= 1u;
         }
         prev_nonlast = !last_group;
         {  // prefetch the next tap-group of the whole kernel into the other buffer
