@@ -1,6 +1,7 @@
 // tcgen05 tensor-core kernels (sm_100a).  Operands: bf16 or fp16 in the interleaved
 // no-swizzle layout of tc_common.cuh; accumulators and the residual stream: fp32 in TMEM.
 #include <cstdio>
+#include <cstdlib>
 #include <stdexcept>
 
 #include "kernels.h"
@@ -36,7 +37,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 //   * the last tap-group of every conv commits one mbarrier per 128-row tile, so the epilogue of
 //     tile m runs while the tensor pipe is still working on tiles m+1.. .
 template <int C, int NT, int FMT>
-__global__ void __launch_bounds__(256, (C == 32 || (C == 64 && NT <= 2)) ? 2 : 1) mrf_tc_kernel(MrfParams p) {
+__global__ void __launch_bounds__(256, ((C == 32 && NT <= 4) || (C == 64 && NT <= 2)) ? 2 : 1) mrf_tc_kernel(MrfParams p) {
   constexpr int R = NT * 128;
   constexpr int CH = C / 8;        // 16-byte K-chunks per row
   constexpr int HC = C / 2;        // columns per epilogue thread (two column halves)
@@ -166,21 +167,29 @@ __global__ void __launch_bounds__(256, (C == 32 || (C == 64 && NT <= 2)) ? 2 : 1
         tc::fence_after_sync();
         if (tid == 0) {
           const uint32_t abase = tc::smem_u32(inbuf), wbase = tc::smem_u32(wbuf + size_t(gi & 1) * wb_bytes);
+          // Issue order: tap / k-step outer, tile inner.  Consecutive MMAs then hit DIFFERENT TMEM
+          // accumulators: a dependent accumulate chain costs ~115 cycles per instruction (measured,
+          // tools/ubench.py), NT independent chains bring it down to ~115/NT.
 #pragma unroll 1
-          for (int m = 0; m < NT; ++m) {
-#pragma unroll 1
-            for (int t = 0; t < ntap; ++t) {
-              const int arow = m * 128 + halo_in + (g0 + t - half) * dil;
+          for (int t = 0; t < ntap; ++t) {
+            const int shift = halo_in + (g0 + t - half) * dil;
 #pragma unroll
-              for (int ks = 0; ks < C / 16; ++ks) {
-                const uint64_t ad = tc::make_desc(abase + uint32_t((ks * 2) * rows_in + arow) * 16u, uint32_t(rows_in) * 16u, 128u);
-                const uint64_t bd = tc::make_desc(wbase + uint32_t((t * CH + ks * 2) * C) * 16u, uint32_t(C) * 16u, 128u);
+            for (int ks = 0; ks < C / 16; ++ks) {
+              const uint64_t bd = tc::make_desc(wbase + uint32_t((t * CH + ks * 2) * C) * 16u, uint32_t(C) * 16u, 128u);
+#pragma unroll
+              for (int m = 0; m < NT; ++m) {
+                const uint64_t ad = tc::make_desc(abase + uint32_t((ks * 2) * rows_in + m * 128 + shift) * 16u,
+                                                  uint32_t(rows_in) * 16u, 128u);
                 tc::mma_f16_ss(tmem + T0 + m * C, ad, bd, idesc, 1u);
               }
             }
-            if (last_group) tc::mma_commit(&tbar[m]);
           }
-          if (!last_group) tc::mma_commit(&gbar[gi & 1]);
+          if (last_group) {
+#pragma unroll
+            for (int m = 0; m < NT; ++m) tc::mma_commit(&tbar[m]);
+          } else {
+            tc::mma_commit(&gbar[gi & 1]);
+          }
         }
         // the buffer the NEXT group will land in was last read by the PREVIOUS group
         if (prev_nonlast) {
@@ -210,16 +219,17 @@ __global__ void __launch_bounds__(256, (C == 32 || (C == 64 && NT <= 2)) ? 2 : 1
           const int r = m * 128 + q * 32 + lane;
           const int g = w0 + r;
           const bool inside = g >= 0 && g < L;
+          float v[NCC][16];
+#pragma unroll
+          for (int cc = 0; cc < NCC; ++cc) tc::tmem_ld16(lane_base + T0 + m * C + hhalf * HC + cc * 16, v[cc]);
+          tc::tmem_ld_wait();
 #pragma unroll
           for (int cc = 0; cc < NCC; ++cc) {
             const int col = hhalf * HC + cc * 16;
-            float v[16];
-            tc::tmem_ld16(lane_base + T0 + m * C + col, v);
-            tc::tmem_ld_wait();
             uint32_t pk[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-              float a = v[2 * e], b = v[2 * e + 1];
+              float a = v[cc][2 * e], b = v[cc][2 * e + 1];
               a = a >= 0.f ? a : 0.1f * a;
               b = b >= 0.f ? b : 0.1f * b;
               pk[e] = inside ? E::pack2(a, b) : 0u;
@@ -319,12 +329,16 @@ void launch_mrf_tc(const MrfParams& p, int C, int fmt, int n_seg, int max_len, c
     if (fmt == 1) launch_mrf_inst<CC, NT, 1>(q, n_seg, max_len, st);                      \
     else launch_mrf_inst<CC, NT, 0>(q, n_seg, max_len, st);                               \
   }
+  static const int nt32 = [] { const char* e = getenv("M3B200_MRF_NT32"); return e ? atoi(e) : 4; }();
+  static const int nt64 = [] { const char* e = getenv("M3B200_MRF_NT64"); return e ? atoi(e) : 2; }();
   if (C == 32) {
     q.wg = pick_wg(16 * 1024);  // whole conv (<= 14 KB) per buffer; ~100 KB/CTA -> 2 CTAs/SM
-    M3_MRF(32, 4)
+    if (nt32 == 8) M3_MRF(32, 8)  // 1 CTA/SM, 8 independent accumulator chains
+    else M3_MRF(32, 4)
   } else if (C == 64) {
     q.wg = pick_wg(16 * 1024);  // 2 taps per buffer; ~109 KB/CTA -> 2 CTAs/SM
-    M3_MRF(64, 2)
+    if (nt64 == 4) M3_MRF(64, 4)  // 1 CTA/SM, 4 chains
+    else M3_MRF(64, 2)
   } else if (C == 128) {
     q.wg = pick_wg(32 * 1024);  // 1 tap per buffer
     M3_MRF(128, 2)

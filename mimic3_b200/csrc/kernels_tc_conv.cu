@@ -117,12 +117,15 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(TcConvParams p, 
           tc::mbar_wait(&full_bar[s], ((it / stages) & 1));
           tc::fence_after_sync();
           const uint32_t wbase = tc::smem_u32(wring + size_t(s) * stage_bytes);
-          for (int m = 0; m < CT_NT; ++m) {
-            const int arow = m * 128 + tap * p.dil;
-            for (int ks = 0; ks < p.K / 16; ++ks) {
+          // k-step outer, tile inner: consecutive MMAs alternate between the two accumulators
+          // (a dependent accumulate chain costs ~115 cycles per instruction, tools/ubench.py)
+          for (int ks = 0; ks < p.K / 16; ++ks) {
+            const uint64_t bd = tc::make_desc(wbase + uint32_t(ks * 2 * NC) * 16u, uint32_t(NC) * 16u, 128u);
+#pragma unroll
+            for (int m = 0; m < CT_NT; ++m) {
+              const int arow = m * 128 + tap * p.dil;
               const uint64_t ad =
                   tc::make_desc(abase + uint32_t((ks * 2) * rows_a + arow) * 16u, uint32_t(rows_a) * 16u, 128u);
-              const uint64_t bd = tc::make_desc(wbase + uint32_t(ks * 2 * NC) * 16u, uint32_t(NC) * 16u, 128u);
               tc::mma_f16_ss(tmem + uint32_t(b * CT_NT + m) * NC, ad, bd, idesc, (tap | ks) ? 1u : 0u);
             }
           }

@@ -149,6 +149,136 @@ double run_probe(int fmt, int K, int N, int taps, int dil, bool with_init, bool 
   return err;
 }
 
+// ---------------------------------------------------------------------------------------
+// Micro-benchmarks (cycles, single CTA): what the MRF design depends on but no document states
+// for sm_100a -- TMEM ld/st rate, SS-mode MMA rate for small N, commit->mbarrier latency.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) tc_ubench_kernel(int mode, int N, int reps, int warps_active,
+                                                        long long* out) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint32_t tmem_slot;
+  __shared__ __align__(8) uint64_t bar;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < 48 * 1024 / 4; i += 256) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;  // fp16 1.0
+  if (warp == 0) tc::tmem_alloc<512>(&tmem_slot);
+  if (tid == 0) {
+    tc::mbar_init(&bar, 1);
+    tc::mbar_fence_init();
+  }
+  tc::fence_async_smem();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t lane_base = tmem + (uint32_t((warp & 3) * 32) << 16);
+  long long t0 = 0, t1 = 0;
+  float v[16];
+  for (int i = 0; i < 16; ++i) v[i] = float(tid + i);
+  if (mode == 0 || mode == 1 || mode == 6) {  // TMEM ld (0: wait per ld, 6: 4 lds per wait) / st (1)
+    __syncthreads();
+    t0 = clock64();
+    if (warp < warps_active) {
+      float acc = 0.f;
+      for (int r = 0; r < reps; ++r) {
+        if (mode == 0) {
+          tc::tmem_ld16(lane_base + ((r * 16) & 255), v);
+          tc::tmem_ld_wait();
+          acc += v[0];
+        } else if (mode == 6) {
+          float a[16], b[16], c[16], d[16];
+          tc::tmem_ld16(lane_base + 0, a);
+          tc::tmem_ld16(lane_base + 16, b);
+          tc::tmem_ld16(lane_base + 32, c);
+          tc::tmem_ld16(lane_base + 48, d);
+          tc::tmem_ld_wait();
+          acc += a[0] + b[0] + c[0] + d[0];
+        } else {
+          tc::tmem_st16(lane_base + ((r * 16) & 255), v);
+        }
+      }
+      if (mode == 1) tc::tmem_st_wait();
+      if (acc == 123.456f) out[63] = 1;
+    }
+    __syncthreads();
+    t1 = clock64();
+  } else if (mode == 2 || mode == 3) {  // MMA stream: reps MMAs then one commit (2), or commit+wait each (3)
+    const uint32_t idesc = tc::make_idesc(128, N, 0);
+    const uint64_t ad = tc::make_desc(tc::smem_u32(smem), 128u * 16u, 128u);
+    const uint64_t bd = tc::make_desc(tc::smem_u32(smem) + 16384u, uint32_t(N) * 16u, 128u);
+    __syncthreads();
+    t0 = clock64();
+    if (tid == 0) {
+      uint32_t ph = 0;
+      for (int r = 0; r < reps; ++r) {
+        tc::mma_f16_ss(tmem, ad, bd, idesc, r ? 1u : 0u);
+        if (mode == 3) {
+          tc::mma_commit(&bar);
+          tc::mbar_wait(&bar, ph);
+          ph ^= 1u;
+        }
+      }
+      if (mode == 2) {
+        tc::mma_commit(&bar);
+        tc::mbar_wait(&bar, 0);
+      }
+    }
+    __syncthreads();
+    t1 = clock64();
+  } else if (mode == 4) {  // one conv-on-one-tile round trip: st -> sync -> MMA(s) -> commit -> wait -> ld
+    const uint32_t idesc = tc::make_idesc(128, N, 0);
+    const uint64_t ad = tc::make_desc(tc::smem_u32(smem), 128u * 16u, 128u);
+    const uint64_t bd = tc::make_desc(tc::smem_u32(smem) + 16384u, uint32_t(N) * 16u, 128u);
+    uint32_t ph = 0;
+    __syncthreads();
+    t0 = clock64();
+    for (int r = 0; r < reps; ++r) {
+      tc::tmem_st16(lane_base, v);
+      tc::tmem_st_wait();
+      tc::fence_before_sync();
+      __syncthreads();
+      tc::fence_after_sync();
+      if (tid == 0) {
+        for (int i = 0; i < 6; ++i) tc::mma_f16_ss(tmem, ad, bd, idesc, 1u);
+        tc::mma_commit(&bar);
+      }
+      tc::mbar_wait(&bar, ph);
+      ph ^= 1u;
+      tc::fence_after_sync();
+      tc::tmem_ld16(lane_base, v);
+      tc::tmem_ld_wait();
+    }
+    __syncthreads();
+    t1 = clock64();
+    if (v[0] == 123.456f) out[63] = 1;
+  } else if (mode == 5) {  // __syncthreads cost
+    __syncthreads();
+    t0 = clock64();
+    for (int r = 0; r < reps; ++r) __syncthreads();
+    t1 = clock64();
+  }
+  if (tid == 0) out[0] = t1 - t0;
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc<512>(tmem);
+}
+
+double run_ubench(int mode, int N, int reps, int warps) {
+  long long* d;
+  cudaMalloc(&d, 64 * sizeof(long long));
+  cudaMemset(d, 0, 64 * sizeof(long long));
+  cudaFuncSetAttribute(tc_ubench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  tc_ubench_kernel<<<1, 256, 64 * 1024>>>(mode, N, reps, warps, d);
+  cudaError_t e = cudaDeviceSynchronize();
+  long long h = -1;
+  if (e == cudaSuccess) cudaMemcpy(&h, d, sizeof h, cudaMemcpyDeviceToHost);
+  else {
+    h = -(long long)e;
+    cudaGetLastError();
+  }
+  cudaFree(d);
+  return double(h) / reps;
+}
+
 }  // namespace
 }  // namespace m3
 
@@ -164,6 +294,23 @@ extern "C" int32_t m3_selftest(int32_t which, double* result) {
     case 5: *result = run_probe(1, 32, 32, 3, 1, false, true); break;     // diagnostic: LBO/SBO swapped
     case 6: *result = run_probe(1, 96, 192, 1, 1, false, false); break;   // 1x1 conv
     case 7: *result = run_probe(0, 64, 64, 7, 3, true, false); break;
+    // micro-benchmarks: cycles per repetition
+    case 100: *result = m3::run_ubench(0, 0, 256, 4); break;   // tcgen05.ld x16 + wait, 4 warps
+    case 101: *result = m3::run_ubench(0, 0, 256, 8); break;   // 8 warps
+    case 102: *result = m3::run_ubench(0, 0, 256, 1); break;   // 1 warp (latency)
+    case 103: *result = m3::run_ubench(6, 0, 256, 4); break;   // 4 x ld16 per wait, 4 warps
+    case 104: *result = m3::run_ubench(6, 0, 256, 8); break;
+    case 105: *result = m3::run_ubench(1, 0, 256, 4); break;   // tcgen05.st x16, 4 warps
+    case 106: *result = m3::run_ubench(1, 0, 256, 8); break;
+    case 110: *result = m3::run_ubench(2, 32, 512, 0); break;  // SS MMA stream, N=32
+    case 111: *result = m3::run_ubench(2, 64, 512, 0); break;
+    case 112: *result = m3::run_ubench(2, 128, 512, 0); break;
+    case 113: *result = m3::run_ubench(2, 256, 512, 0); break;
+    case 120: *result = m3::run_ubench(3, 32, 64, 0); break;   // MMA + commit + wait latency
+    case 121: *result = m3::run_ubench(3, 128, 64, 0); break;
+    case 130: *result = m3::run_ubench(4, 32, 64, 0); break;   // st/sync/6 MMA/commit/wait/ld round trip
+    case 131: *result = m3::run_ubench(4, 128, 64, 0); break;
+    case 140: *result = m3::run_ubench(5, 0, 256, 0); break;   // __syncthreads
     default: return M3_ERR_INVALID;
   }
   return M3_OK;
