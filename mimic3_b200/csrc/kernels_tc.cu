@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(256, ((C == 32 && NT <= 4) || (C == 64 && NT <
   if (o0 >= L) return;
   const long long base = (long long)p.seg_off[seg] * p.scale;
   const int w0 = o0 - p.H;
-  const int ROWSX = R + 2 * p.HX, ROWSY = R + 2 * p.HY;
+  const int ROWSX = (R + 2 * p.HX) | 1, ROWSY = (R + 2 * p.HY) | 1;  // odd pitches: conflict-free chunk-major stores
   const uint32_t wb_bytes = uint32_t(p.wg) * C * C * 2;
   uint8_t* bufX = smem;
   uint8_t* bufY = bufX + size_t(CH) * ROWSX * 16;
@@ -107,20 +107,40 @@ __global__ void __launch_bounds__(256, ((C == 32 && NT <= 4) || (C == 64 && NT <
     }
   }
   // ---- lrelu(x) of the window (+halo) as the 16-bit A operand ----------------------------------
-  for (int idx = tid; idx < CH * ROWSX; idx += 256) {
-    const int c8 = idx / ROWSX, rr = idx - c8 * ROWSX;
-    const int g = w0 - p.HX + rr;
-    uint4 pk = make_uint4(0u, 0u, 0u, 0u);
-    if (g >= 0 && g < L) {
-      const float4 a = *reinterpret_cast<const float4*>(xg + (base + g) * C + c8 * 8);
-      const float4 b = *reinterpret_cast<const float4*>(xg + (base + g) * C + c8 * 8 + 4);
-      auto lr = [](float v) { return v >= 0.f ? v : 0.1f * v; };
-      pk.x = E::pack2(lr(a.x), lr(a.y));
-      pk.y = E::pack2(lr(a.z), lr(a.w));
-      pk.z = E::pack2(lr(b.x), lr(b.y));
-      pk.w = E::pack2(lr(b.z), lr(b.w));
+  // item = (row, 8-channel chunk), chunk fastest (coalesced reads); four items in flight per thread
+  {
+    const int items = CH * ROWSX;
+    auto lr = [](float v) { return v >= 0.f ? v : 0.1f * v; };
+    for (int i0 = tid; i0 < items; i0 += 4 * 256) {
+      float4 a[4], b[4];
+      int dsti[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int idx = i0 + u * 256;
+        a[u] = b[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        dsti[u] = -1;
+        if (idx < items) {
+          const int rr = idx / CH, c8 = idx - rr * CH;
+          dsti[u] = c8 * ROWSX + rr;
+          const int g = w0 - p.HX + rr;
+          if (g >= 0 && g < L) {
+            const float* src = xg + (base + g) * C + c8 * 8;
+            a[u] = *reinterpret_cast<const float4*>(src);
+            b[u] = *reinterpret_cast<const float4*>(src + 4);
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (dsti[u] < 0) continue;
+        uint4 pk;
+        pk.x = E::pack2(lr(a[u].x), lr(a[u].y));
+        pk.y = E::pack2(lr(a[u].z), lr(a[u].w));
+        pk.z = E::pack2(lr(b[u].x), lr(b[u].y));
+        pk.w = E::pack2(lr(b[u].z), lr(b[u].w));
+        *reinterpret_cast<uint4*>(bufX + size_t(dsti[u]) * 16) = pk;
+      }
     }
-    *reinterpret_cast<uint4*>(bufX + size_t(idx) * 16) = pk;
   }
   tc::fence_before_sync();
   __syncthreads();
@@ -165,7 +185,7 @@ __global__ void __launch_bounds__(256, ((C == 32 && NT <= 4) || (C == 64 && NT <
         tc::fence_before_sync();
         __syncthreads();
         tc::fence_after_sync();
-        if (tid == 0) {
+        if (warp == 0 && tc::elect_one()) {  // warp-uniform branch + elect.sync: no per-MMA waterfall loop
           const uint32_t abase = tc::smem_u32(inbuf), wbase = tc::smem_u32(wbuf + size_t(gi & 1) * wb_bytes);
           // Issue order: tap / k-step outer, tile inner.  Consecutive MMAs then hit DIFFERENT TMEM
           // accumulators: a dependent accumulate chain costs ~115 cycles per instruction (measured,
@@ -295,7 +315,7 @@ static void launch_mrf_inst(const MrfParams& p, int n_seg, int max_len, cudaStre
   MrfParams q = p;
   q.stride = R - 2 * p.H;
   if (q.stride <= 0) throw std::runtime_error("mrf_tc: receptive field exceeds the window");
-  const size_t smem = size_t(C / 8) * 16 * (size_t(R + 2 * p.HX) + size_t(R + 2 * p.HY)) + size_t(2) * p.wg * C * C * 2;
+  const size_t smem = size_t(C / 8) * 16 * (size_t((R + 2 * p.HX) | 1) + size_t((R + 2 * p.HY) | 1)) + size_t(2) * p.wg * C * C * 2;
   auto kern = mrf_tc_kernel<C, NT, FMT>;
   static thread_local size_t configured = 0;
   if (configured < smem) {

@@ -63,24 +63,43 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(TcConvParams p, 
     tc::mbar_fence_init();
   }
   // ---- stage the A operand: input rows [t0 - halo_l, t0 - halo_l + rows_a) x K ------------------
+  // Item = (row, 8-channel chunk), chunk fastest: a warp reads whole rows (coalesced 32 B per lane);
+  // rows_a is odd so the 16-byte smem stores of 8 neighbouring chunks fall into distinct banks.
+  // Four items per thread are in flight at once (the loop is a chain of L2 round trips otherwise).
   {
     const int halo_l = p.pad_left * p.dil;
     const float slope = p.in_slope;
-    for (int idx = tid; idx < CH * rows_a; idx += CT_THREADS) {
-      const int c8 = idx / rows_a, rr = idx - c8 * rows_a;
-      const int ti = t0 - halo_l + rr;
-      uint4 pk = make_uint4(0u, 0u, 0u, 0u);
-      if (ti >= 0 && ti < in_len) {
-        const float* src = p.in + (in_base + ti) * (long long)p.in_stride + p.in_coff + c8 * 8;
-        const float4 a = *reinterpret_cast<const float4*>(src);
-        const float4 b = *reinterpret_cast<const float4*>(src + 4);
-        auto lr = [slope](float v) { return v >= 0.f ? v : slope * v; };
-        pk.x = E::pack2(lr(a.x), lr(a.y));
-        pk.y = E::pack2(lr(a.z), lr(a.w));
-        pk.z = E::pack2(lr(b.x), lr(b.y));
-        pk.w = E::pack2(lr(b.z), lr(b.w));
+    const int items = CH * rows_a;
+    auto lr = [slope](float v) { return v >= 0.f ? v : slope * v; };
+    for (int i0 = tid; i0 < items; i0 += 4 * CT_THREADS) {
+      float4 a[4], b[4];
+      int dsti[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int idx = i0 + u * CT_THREADS;
+        a[u] = b[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        dsti[u] = -1;
+        if (idx < items) {
+          const int rr = idx / CH, c8 = idx - rr * CH;
+          dsti[u] = c8 * rows_a + rr;
+          const int ti = t0 - halo_l + rr;
+          if (ti >= 0 && ti < in_len) {
+            const float* src = p.in + (in_base + ti) * (long long)p.in_stride + p.in_coff + c8 * 8;
+            a[u] = *reinterpret_cast<const float4*>(src);
+            b[u] = *reinterpret_cast<const float4*>(src + 4);
+          }
+        }
       }
-      *reinterpret_cast<uint4*>(bufA + size_t(idx) * 16) = pk;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (dsti[u] < 0) continue;
+        uint4 pk;
+        pk.x = E::pack2(lr(a[u].x), lr(a[u].y));
+        pk.y = E::pack2(lr(a[u].z), lr(a[u].w));
+        pk.z = E::pack2(lr(b[u].x), lr(b[u].y));
+        pk.w = E::pack2(lr(b[u].z), lr(b[u].w));
+        *reinterpret_cast<uint4*>(bufA + size_t(dsti[u]) * 16) = pk;
+      }
     }
   }
   tc::fence_async_smem();
@@ -211,30 +230,36 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(TcConvParams p, 
             }
             if (t >= out_len) continue;
             const long long orow = out_base + t;
-#pragma unroll 1
-            for (int e = 0; e < 16; e += 4) {
-              const int n = n0 + e;
-              if (n >= p.N) break;
+            float4* d4[4];
+            float4 cur[4];
+#pragma unroll
+            for (int e4 = 0; e4 < 4; ++e4) {  // all read-modify-write operands in flight together
+              const int n = n0 + e4 * 4;
+              d4[e4] = nullptr;
+              if (n < p.N) {
+                float* dst = n < p.split ? p.out + orow * p.out_stride + p.out_coff + n
+                                         : p.out2 + orow * p.out2_stride + (n - p.split);
+                d4[e4] = reinterpret_cast<float4*>(dst);
+                if (p.epi != TC_STORE) cur[e4] = *d4[e4];
+              }
+            }
+#pragma unroll
+            for (int e4 = 0; e4 < 4; ++e4) {
+              if (!d4[e4]) continue;
+              const int n = n0 + e4 * 4;
               float o[4];
 #pragma unroll
               for (int f = 0; f < 4; ++f) {
-                o[f] = v[e + f];
+                o[f] = v[e4 * 4 + f];
                 if (p.bias) o[f] += p.bias[n + f];
                 if (p.ubias) o[f] += p.ubias[(long long)seg * p.ub_stride + n + f];
               }
-              float* dst = n < p.split ? p.out + orow * p.out_stride + p.out_coff + n
-                                       : p.out2 + orow * p.out2_stride + (n - p.split);
-              float4* d4 = reinterpret_cast<float4*>(dst);
               if (p.epi == TC_STORE) {
-                *d4 = make_float4(o[0], o[1], o[2], o[3]);
-              } else {
-                float4 cur = *d4;
-                if (p.epi == TC_RES_SKIP) {
-                  cur.x += o[0]; cur.y += o[1]; cur.z += o[2]; cur.w += o[3];
-                } else {  // TC_SUB
-                  cur.x -= o[0]; cur.y -= o[1]; cur.z -= o[2]; cur.w -= o[3];
-                }
-                *d4 = cur;
+                *d4[e4] = make_float4(o[0], o[1], o[2], o[3]);
+              } else if (p.epi == TC_RES_SKIP) {
+                *d4[e4] = make_float4(cur[e4].x + o[0], cur[e4].y + o[1], cur[e4].z + o[2], cur[e4].w + o[3]);
+              } else {  // TC_SUB
+                *d4[e4] = make_float4(cur[e4].x - o[0], cur[e4].y - o[1], cur[e4].z - o[2], cur[e4].w - o[3]);
               }
             }
           }
@@ -253,7 +278,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(TcConvParams p, 
 bool conv_tc_supported(int K, int NC, int taps, int dil) {
   if (K % 16 || K < 16 || K > 512) return false;
   if (NC % 32 || NC < 32 || NC > 128) return false;  // 2 buffers x 2 tiles x NC <= 512 TMEM columns
-  const size_t a_bytes = size_t(K / 8) * (CT_R + (taps - 1) * dil) * 16 + 128;
+  const size_t a_bytes = size_t(K / 8) * ((CT_R + (taps - 1) * dil) | 1) * 16 + 128;
   const size_t stage = size_t(K) * NC * 2;
   return a_bytes + 2 * stage <= size_t(CT_SMEM_MAX);
 }
@@ -261,7 +286,7 @@ bool conv_tc_supported(int K, int NC, int taps, int dil) {
 void launch_conv_tc(const TcConvParams& p, int fmt, int n_seg, int max_seg_len, cudaStream_t st) {
   const int rows = max_seg_len * p.in_scale + p.rows_extra;
   if (rows <= 0 || n_seg <= 0) return;
-  const int rows_a = CT_R + (p.taps - 1) * p.dil;
+  const int rows_a = (CT_R + (p.taps - 1) * p.dil) | 1;  // odd row pitch: conflict-free chunk-major smem stores
   const size_t a_bytes = (size_t(p.K / 8) * rows_a * 16 + 127) & ~size_t(127);
   const size_t stage = size_t(p.K) * p.NC * 2;
   int stages = int((size_t(CT_SMEM_MAX) - a_bytes) / stage);

@@ -224,6 +224,26 @@ __global__ void __launch_bounds__(256) tc_ubench_kernel(int mode, int N, int rep
     }
     __syncthreads();
     t1 = clock64();
+  } else if (mode == 7 || mode == 8) {  // warp-uniform branch + elect.sync issue (no waterfall loop)
+    const uint32_t idesc = tc::make_idesc(128, N, 0);
+    const uint64_t ad = tc::make_desc(tc::smem_u32(smem), 128u * 16u, 128u);
+    const uint64_t bd = tc::make_desc(tc::smem_u32(smem) + 16384u, uint32_t(N) * 16u, 128u);
+    __syncthreads();
+    t0 = clock64();
+    if (warp == 1) {
+      if (tc::elect_one()) {
+        for (int r = 0; r < reps; r += 4) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            tc::mma_f16_ss(tmem + (mode == 8 ? uint32_t(u * 128) : 0u), ad, bd, idesc, r ? 1u : 0u);
+        }
+        tc::mma_commit(&bar);
+        tc::mbar_wait(&bar, 0);
+      }
+      __syncwarp();
+    }
+    __syncthreads();
+    t1 = clock64();
   } else if (mode == 4) {  // one conv-on-one-tile round trip: st -> sync -> MMA(s) -> commit -> wait -> ld
     const uint32_t idesc = tc::make_idesc(128, N, 0);
     const uint64_t ad = tc::make_desc(tc::smem_u32(smem), 128u * 16u, 128u);
@@ -306,6 +326,11 @@ extern "C" int32_t m3_selftest(int32_t which, double* result) {
     case 111: *result = m3::run_ubench(2, 64, 512, 0); break;
     case 112: *result = m3::run_ubench(2, 128, 512, 0); break;
     case 113: *result = m3::run_ubench(2, 256, 512, 0); break;
+    case 114: *result = m3::run_ubench(7, 32, 512, 0); break;   // elect-issued, one accumulator, N=32
+    case 115: *result = m3::run_ubench(7, 128, 512, 0); break;
+    case 116: *result = m3::run_ubench(8, 32, 512, 0); break;   // elect-issued, 4 accumulators, N=32
+    case 117: *result = m3::run_ubench(8, 64, 512, 0); break;
+    case 118: *result = m3::run_ubench(8, 128, 512, 0); break;
     case 120: *result = m3::run_ubench(3, 32, 64, 0); break;   // MMA + commit + wait latency
     case 121: *result = m3::run_ubench(3, 128, 64, 0); break;
     case 130: *result = m3::run_ubench(4, 32, 64, 0); break;   // st/sync/6 MMA/commit/wait/ld round trip
