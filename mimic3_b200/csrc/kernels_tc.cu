@@ -36,11 +36,12 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 //   * conv weights stream through a 2-deep cp.async ring, one tap-group ahead of the MMAs;
 //   * the last tap-group of every conv commits one mbarrier per 128-row tile, so the epilogue of
 //     tile m runs while the tensor pipe is still working on tiles m+1.. .
-template <int C, int NT, int FMT>
-__global__ void __launch_bounds__(256, ((C == 32 && NT <= 4) || (C == 64 && NT <= 2)) ? 2 : 1) mrf_tc_kernel(MrfParams p) {
+template <int C, int NT, int FMT, int NW, int MINB>
+__global__ void __launch_bounds__(NW * 32, MINB) mrf_tc_kernel(MrfParams p) {
+  constexpr int NTHR = NW * 32;
   constexpr int R = NT * 128;
   constexpr int CH = C / 8;        // 16-byte K-chunks per row
-  constexpr int HC = C / 2;        // columns per epilogue thread (two column halves)
+  constexpr int HC = C / (NW / 4); // columns per epilogue thread (NW/4 column groups)
   constexpr int NCC = HC / 16;     // 16-column groups per thread
   constexpr int TCOLS_RAW = 2 * NT * C;
   constexpr int TCOLS = TCOLS_RAW <= 32 ? 32 : TCOLS_RAW <= 64 ? 64 : TCOLS_RAW <= 128 ? 128 : TCOLS_RAW <= 256 ? 256 : 512;
@@ -50,6 +51,7 @@ __global__ void __launch_bounds__(256, ((C == 32 && NT <= 4) || (C == 64 && NT <
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(8) uint64_t gbar[2], tbar[NT];
+  __shared__ float sbias[5][C];  // first-conv bias of each resblock (<= 4) + the summed late bias
 
   const int seg = blockIdx.y;
   const int L = p.seg_len[seg] * p.scale;
@@ -74,11 +76,15 @@ __global__ void __launch_bounds__(256, ((C == 32 && NT <= 4) || (C == 64 && NT <
     const uint4* __restrict__ src = reinterpret_cast<const uint4*>(group_src(j, d, g0));
     uint4* dst = reinterpret_cast<uint4*>(wbuf + size_t(buf) * wb_bytes);
     const int n16 = ntap * C * C / 8;
-    for (int i = tid; i < n16; i += 256) cp_async16(dst + i, src + i);
+    for (int i = tid; i < n16; i += NTHR) cp_async16(dst + i, src + i);
     cp_async_commit();
   };
   prefetch(0, 0, 0, 0);
 
+  for (int i = tid; i < 5 * C; i += NTHR) {
+    const int j = i / C, c = i - j * C;
+    sbias[j][c] = j < 4 ? (j < p.nk ? p.bias[j][0][c] : 0.f) : p.late_bias[c];
+  }
   if (warp == 0) tc::tmem_alloc<TCOLS>(&tmem_slot);
   if (tid == 0) {
     tc::mbar_init(&gbar[0], 1);
@@ -111,12 +117,12 @@ __global__ void __launch_bounds__(256, ((C == 32 && NT <= 4) || (C == 64 && NT <
   {
     const int items = CH * ROWSX;
     auto lr = [](float v) { return v >= 0.f ? v : 0.1f * v; };
-    for (int i0 = tid; i0 < items; i0 += 4 * 256) {
+    for (int i0 = tid; i0 < items; i0 += 4 * NTHR) {
       float4 a[4], b[4];
       int dsti[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const int idx = i0 + u * 256;
+        const int idx = i0 + u * NTHR;
         a[u] = b[u] = make_float4(0.f, 0.f, 0.f, 0.f);
         dsti[u] = -1;
         if (idx < items) {
@@ -158,7 +164,7 @@ __global__ void __launch_bounds__(256, ((C == 32 && NT <= 4) || (C == 64 && NT <
     const int half = (k - 1) / 2;
     // ---- T <- x + bias of the first conv (registers -> TMEM) -----------------------------------
     {
-      const float* __restrict__ b0 = p.bias[j][0];
+      const float* b0 = sbias[j];  // warp-uniform addresses: broadcast LDS, no global latency
 #pragma unroll
       for (int m = 0; m < NT; ++m) {
 #pragma unroll
@@ -261,6 +267,7 @@ __global__ void __launch_bounds__(256, ((C == 32 && NT <= 4) || (C == 64 && NT <
         }
       } else {
         const bool first = j == 0, last = j == p.nk - 1;
+        const float* lbv = sbias[4];
 #pragma unroll 1
         for (int m = 0; m < NT; ++m) {
           tc::mbar_wait(&tbar[m], tphase);
@@ -286,14 +293,13 @@ __global__ void __launch_bounds__(256, ((C == 32 && NT <= 4) || (C == 64 && NT <
               tc::tmem_st16(lane_base + S0 + m * C + col, v);
             } else if (store) {
               float4* dst = reinterpret_cast<float4*>(p.out + (base + g) * C + col);
-              const float* lb = p.late_bias;
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 float4 o;
-                o.x = (v[e * 4 + 0] + lb[col + e * 4 + 0]) * p.inv_nk;
-                o.y = (v[e * 4 + 1] + lb[col + e * 4 + 1]) * p.inv_nk;
-                o.z = (v[e * 4 + 2] + lb[col + e * 4 + 2]) * p.inv_nk;
-                o.w = (v[e * 4 + 3] + lb[col + e * 4 + 3]) * p.inv_nk;
+                o.x = (v[e * 4 + 0] + lbv[col + e * 4 + 0]) * p.inv_nk;
+                o.y = (v[e * 4 + 1] + lbv[col + e * 4 + 1]) * p.inv_nk;
+                o.z = (v[e * 4 + 2] + lbv[col + e * 4 + 2]) * p.inv_nk;
+                o.w = (v[e * 4 + 3] + lbv[col + e * 4 + 3]) * p.inv_nk;
                 dst[e] = o;
               }
             }
@@ -309,14 +315,14 @@ __global__ void __launch_bounds__(256, ((C == 32 && NT <= 4) || (C == 64 && NT <
   if (warp == 0) tc::tmem_dealloc<TCOLS>(tmem);
 }
 
-template <int C, int NT, int FMT>
+template <int C, int NT, int FMT, int NW, int MINB>
 static void launch_mrf_inst(const MrfParams& p, int n_seg, int max_len, cudaStream_t st) {
   const int R = NT * 128;
   MrfParams q = p;
   q.stride = R - 2 * p.H;
   if (q.stride <= 0) throw std::runtime_error("mrf_tc: receptive field exceeds the window");
   const size_t smem = size_t(C / 8) * 16 * (size_t((R + 2 * p.HX) | 1) + size_t((R + 2 * p.HY) | 1)) + size_t(2) * p.wg * C * C * 2;
-  auto kern = mrf_tc_kernel<C, NT, FMT>;
+  auto kern = mrf_tc_kernel<C, NT, FMT, NW, MINB>;
   static thread_local size_t configured = 0;
   if (configured < smem) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
@@ -325,7 +331,7 @@ static void launch_mrf_inst(const MrfParams& p, int n_seg, int max_len, cudaStre
   }
   const int L = max_len * p.scale;
   dim3 grid((L + q.stride - 1) / q.stride, n_seg);
-  kern<<<grid, 256, smem, st>>>(q);
+  kern<<<grid, NW * 32, smem, st>>>(q);
   post_launch("mrf_tc_kernel", st);
 }
 
@@ -344,24 +350,25 @@ void launch_mrf_tc(const MrfParams& p, int C, int fmt, int n_seg, int max_len, c
     for (int j = 0; j < p.nk; ++j) kmax = max(kmax, p.k[j]);
     return max(1, min(kmax, bytes_budget / (C * C * 2)));
   };
-#define M3_MRF(CC, NT)                                                                    \
+#define M3_MRF(CC, NT, NW, MINB)                                                          \
   {                                                                                       \
-    if (fmt == 1) launch_mrf_inst<CC, NT, 1>(q, n_seg, max_len, st);                      \
-    else launch_mrf_inst<CC, NT, 0>(q, n_seg, max_len, st);                               \
+    if (fmt == 1) launch_mrf_inst<CC, NT, 1, NW, MINB>(q, n_seg, max_len, st);            \
+    else launch_mrf_inst<CC, NT, 0, NW, MINB>(q, n_seg, max_len, st);                     \
   }
   static const int nt32 = [] { const char* e = getenv("M3B200_MRF_NT32"); return e ? atoi(e) : 4; }();
   static const int nt64 = [] { const char* e = getenv("M3B200_MRF_NT64"); return e ? atoi(e) : 2; }();
   if (C == 32) {
     q.wg = pick_wg(16 * 1024);  // whole conv (<= 14 KB) per buffer; ~100 KB/CTA -> 2 CTAs/SM
-    if (nt32 == 8) M3_MRF(32, 8)  // 1 CTA/SM, 8 independent accumulator chains
-    else M3_MRF(32, 4)
+    if (nt32 == 2) M3_MRF(32, 2, 4, 4)       // 128-thread CTAs, 4 per SM (more latency chains in flight)
+    else if (nt32 == 3) M3_MRF(32, 3, 4, 3)  // 128-thread CTAs, 3 per SM
+    else M3_MRF(32, 4, 8, 2)
   } else if (C == 64) {
     q.wg = pick_wg(16 * 1024);  // 2 taps per buffer; ~109 KB/CTA -> 2 CTAs/SM
-    if (nt64 == 4) M3_MRF(64, 4)  // 1 CTA/SM, 4 chains
-    else M3_MRF(64, 2)
+    if (nt64 == 4) M3_MRF(64, 4, 8, 1)
+    else M3_MRF(64, 2, 8, 2)
   } else if (C == 128) {
     q.wg = pick_wg(32 * 1024);  // 1 tap per buffer
-    M3_MRF(128, 2)
+    M3_MRF(128, 2, 8, 1)
   } else {
     throw std::runtime_error("mrf_tc: unsupported channel count");
   }

@@ -224,26 +224,31 @@ __global__ void __launch_bounds__(256) tc_ubench_kernel(int mode, int N, int rep
     }
     __syncthreads();
     t1 = clock64();
-  } else if (mode == 7 || mode == 8) {  // warp-uniform branch + elect.sync issue (no waterfall loop)
-    const uint32_t idesc = tc::make_idesc(128, N, 0);
+  } else if (mode >= 7 && mode <= 9) {  // warp-uniform branch + elect.sync issue (no waterfall loop)
+    // mode 7: one accumulator; 8: four accumulators round robin; 9: like 8 with M=64
+    const uint32_t idesc = tc::make_idesc(mode == 9 ? 64 : 128, N, 0);
     const uint64_t ad = tc::make_desc(tc::smem_u32(smem), 128u * 16u, 128u);
     const uint64_t bd = tc::make_desc(tc::smem_u32(smem) + 16384u, uint32_t(N) * 16u, 128u);
     __syncthreads();
-    t0 = clock64();
-    if (warp == 1) {
+    long long e0 = 0, e1 = 0;
+    if (warp == 0) {
       if (tc::elect_one()) {
+        e0 = clock64();
         for (int r = 0; r < reps; r += 4) {
 #pragma unroll
           for (int u = 0; u < 4; ++u)
-            tc::mma_f16_ss(tmem + (mode == 8 ? uint32_t(u * 128) : 0u), ad, bd, idesc, r ? 1u : 0u);
+            tc::mma_f16_ss(tmem + (mode >= 8 ? uint32_t(u * 128) : 0u), ad, bd, idesc, r ? 1u : 0u);
         }
         tc::mma_commit(&bar);
         tc::mbar_wait(&bar, 0);
+        e1 = clock64();
+        out[1] = e1 - e0;
       }
       __syncwarp();
     }
     __syncthreads();
-    t1 = clock64();
+    t0 = 0;
+    t1 = 0;
   } else if (mode == 4) {  // one conv-on-one-tile round trip: st -> sync -> MMA(s) -> commit -> wait -> ld
     const uint32_t idesc = tc::make_idesc(128, N, 0);
     const uint64_t ad = tc::make_desc(tc::smem_u32(smem), 128u * 16u, 128u);
@@ -276,7 +281,7 @@ __global__ void __launch_bounds__(256) tc_ubench_kernel(int mode, int N, int rep
     for (int r = 0; r < reps; ++r) __syncthreads();
     t1 = clock64();
   }
-  if (tid == 0) out[0] = t1 - t0;
+  if (tid == 0 && !(mode >= 7 && mode <= 9)) out[1] = t1 - t0;
   tc::fence_before_sync();
   __syncthreads();
   if (warp == 0) tc::tmem_dealloc<512>(tmem);
@@ -290,7 +295,7 @@ double run_ubench(int mode, int N, int reps, int warps) {
   tc_ubench_kernel<<<1, 256, 64 * 1024>>>(mode, N, reps, warps, d);
   cudaError_t e = cudaDeviceSynchronize();
   long long h = -1;
-  if (e == cudaSuccess) cudaMemcpy(&h, d, sizeof h, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) cudaMemcpy(&h, d + 1, sizeof h, cudaMemcpyDeviceToHost);
   else {
     h = -(long long)e;
     cudaGetLastError();
@@ -331,6 +336,7 @@ extern "C" int32_t m3_selftest(int32_t which, double* result) {
     case 116: *result = m3::run_ubench(8, 32, 512, 0); break;   // elect-issued, 4 accumulators, N=32
     case 117: *result = m3::run_ubench(8, 64, 512, 0); break;
     case 118: *result = m3::run_ubench(8, 128, 512, 0); break;
+    case 119: *result = m3::run_ubench(9, 32, 512, 0); break;   // M=64, 4 accumulators
     case 120: *result = m3::run_ubench(3, 32, 64, 0); break;   // MMA + commit + wait latency
     case 121: *result = m3::run_ubench(3, 128, 64, 0); break;
     case 130: *result = m3::run_ubench(4, 32, 64, 0); break;   // st/sync/6 MMA/commit/wait/ld round trip

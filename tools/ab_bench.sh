@@ -1,6 +1,6 @@
 #!/bin/bash
 # A/B of MRF tile configurations (stage times only)
-for cfg in "4 2" "8 2" "4 4" "8 4"; do
+for cfg in "4 2" "2 2" "3 2"; do
   set -- $cfg
   echo "== NT32=$1 NT64=$2"
   M3B200_MRF_NT32=$1 M3B200_MRF_NT64=$2 timeout 200 python bench.py --steps 3 --warmup 2 --no-cpu-baseline 2>/dev/null | python -c "

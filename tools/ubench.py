@@ -8,7 +8,7 @@ names = {100: "tcgen05.ld x16 + wait, 4 warps", 101: "same, 8 warps", 102: "same
          110: "SS MMA M128 N32 K16 stream", 111: "SS MMA N64", 112: "SS MMA N128", 113: "SS MMA N256",
          114: "elect-issued MMA N32, 1 accumulator", 115: "elect-issued MMA N128, 1 accumulator",
          116: "elect-issued MMA N32, 4 accumulators", 117: "elect-issued MMA N64, 4 accumulators",
-         118: "elect-issued MMA N128, 4 accumulators",
+         118: "elect-issued MMA N128, 4 accumulators", 119: "elect-issued MMA M64 N32, 4 accumulators",
          120: "MMA+commit+wait N32", 121: "MMA+commit+wait N128", 130: "st/sync/6xMMA/commit/wait/ld N32",
          131: "same N128", 140: "__syncthreads (256 thr)"}
 for k, n in names.items():
