@@ -639,6 +639,30 @@ struct Run {
   }
   void conv(const ConvParams& p, const Segs& s) const { launch_conv(p, s.n, s.max_len, st); }
 
+  // token-level fp32 convs over packed rows
+  const int4* rowinfo = nullptr;
+  int n_rows = 0;
+  void row_conv(const Lin& l, const float* in, int in_stride, float* out, int out_stride, int act = 0,
+                const float* ub = nullptr, int ub_stride = 0) const {
+    RowConvParams p;
+    p.in = in;
+    p.in_stride = in_stride;
+    p.Cin = l.cin;
+    p.W = l.w;
+    p.Cout = l.cout;
+    p.taps = l.taps;
+    p.pad_left = (l.taps - 1) / 2;
+    p.bias = l.b;
+    p.ubias = ub;
+    p.ub_stride = ub_stride;
+    p.act = act;
+    p.out = out;
+    p.out_stride = out_stride;
+    p.rowinfo = rowinfo;
+    p.rows = n_rows;
+    launch_row_conv(p, st);
+  }
+
   bool tc_ok(const TcConvW& t) const { return dv.use_tc && t.ok; }
   TcConvParams base_tc(const TcConvW& t, const float* bias, const float* in, int in_stride, float* out,
                        int out_stride, const Segs& s, int scale) const {
@@ -679,8 +703,7 @@ struct Run {
     int dil = 1;
     for (int i = 0; i < 3; ++i) {
       launch_dds_sep(x, d.sep_w[i], d.sep_b[i], d.n1g[i], d.n1b[i], tmp1, C, dil, s.off, s.len, s.n, s.max_len, st);
-      ConvParams p = base_conv(d.c1x1[i], tmp1, C, tmp2, C, s, 1);
-      conv(p, s);
+      row_conv(d.c1x1[i], tmp1, C, tmp2, C);
       launch_layernorm(tmp2, nullptr, x, d.n2g[i], d.n2b[i], x, rows, C, 1, st);
       dil *= 3;
     }
@@ -752,7 +775,7 @@ Result* run_inference(Voice& v, const int64_t* ids, const int64_t* lengths, int 
   // ---------------- phase 1 workspace (token level) ----------------
   {
     size_t fl = size_t(NT) * (size_t(H) * 3 + 3 * H + Ff + 2 * I + size_t(Fd) * 4 + 40) + size_t(batch) * (G + dv.n_cond + 8);
-    size_t bytes = fl * 4 + size_t(batch) * t_stride * 8 + size_t(batch) * 64 + (1 << 16) + 512 * 64;
+    size_t bytes = fl * 4 + size_t(batch) * t_stride * 8 + size_t(batch) * 64 + (1 << 16) + 512 * 64 + size_t(NT) * 16;
     cx.a1.reserve(bytes);
   }
   Arena& A = cx.a1;
@@ -788,6 +811,12 @@ Result* run_inference(Voice& v, const int64_t* ids, const int64_t* lengths, int 
   }
   Segs tok{d_tok_off, d_tok_len, batch, Tmax};
   Segs one{d_one, d_one + 1, 1, batch};
+  {
+    int4* d_rowinfo = A.alloc<int4>(NT);
+    launch_fill_rowinfo(d_rowinfo, d_tok_off, d_tok_len, batch, Tmax, st);
+    R.rowinfo = d_rowinfo;
+    R.n_rows = NT;
+  }
 
   // ---------------- speaker conditioning ----------------
   float* d_cond = nullptr;  // [batch][n_cond]
@@ -813,20 +842,16 @@ Result* run_inference(Voice& v, const int64_t* ids, const int64_t* lengths, int 
   launch_embedding(d_ids, t_stride, dv.emb, c.num_symbols, sqrtf(float(H)), x, H, d_tok_off, d_tok_len, batch, Tmax, st);
   for (int l = 0; l < c.n_layers; ++l) {
     const EncLayerW& L = dv.enc[l];
-    R.conv(R.base_conv(L.qkv, x, H, qkv, 3 * H, tok, 1), tok);
+    R.row_conv(L.qkv, x, H, qkv, 3 * H);
     launch_attention(qkv, L.ek, L.ev, att, H, c.n_heads, dv.window, d_tok_off, d_tok_len, batch, Tmax, st);
-    R.conv(R.base_conv(L.o, att, H, y, H, tok, 1), tok);
+    R.row_conv(L.o, att, H, y, H);
     launch_layernorm(x, y, nullptr, L.g1, L.b1, x, NT, H, 0, st);
-    {
-      ConvParams p = R.base_conv(L.ffn1, x, H, ffn, Ff, tok, 1);
-      p.act = 1;
-      R.conv(p, tok);
-      // attentions.FFN "same" padding: pad_l = (k-1)//2, pad_r = k//2  -> pad_left as base_conv
-    }
-    R.conv(R.base_conv(L.ffn2, ffn, Ff, y, H, tok, 1), tok);
+    // attentions.FFN "same" padding: pad_l = (k-1)//2, pad_r = k//2
+    R.row_conv(L.ffn1, x, H, ffn, Ff, 1);
+    R.row_conv(L.ffn2, ffn, Ff, y, H);
     launch_layernorm(x, y, nullptr, L.g2, L.b2, x, NT, H, 0, st);
   }
-  R.conv(R.base_conv(dv.enc_proj, x, H, stats, 2 * I, tok, 1), tok);
+  R.row_conv(dv.enc_proj, x, H, stats, 2 * I);
   R.mark("text_encoder");
   R.dump("x", x, NT, H);
   R.dump("stats", stats, NT, 2 * I);
@@ -840,14 +865,9 @@ Result* run_inference(Voice& v, const int64_t* ids, const int64_t* lengths, int 
     float* t2 = A.alloc<float>(size_t(NT) * Fd);
     float* pr = A.alloc<float>(size_t(NT) * 32);
     float* z = A.alloc<float>(size_t(NT) * 2);
-    {
-      ConvParams p = R.base_conv(dv.dp_pre, x, H, h, Fd, tok, 1);
-      p.ubias = ubias(dv.dp_cond_off);
-      p.ub_stride = dv.n_cond;
-      R.conv(p, tok);
-    }
+    R.row_conv(dv.dp_pre, x, H, h, Fd, 0, ubias(dv.dp_cond_off), dv.n_cond);
     R.dds(dv.dp_dds, h, t1, t2, Fd, tok, NT);
-    R.conv(R.base_conv(dv.dp_proj, h, Fd, t1, Fd, tok, 1), tok);
+    R.row_conv(dv.dp_proj, h, Fd, t1, Fd);
     float* hc = t1;  // conditioning for the conv flows
     float* s1 = h;   // h is free now: reuse as scratch
     launch_sdp_noise(z, noise_w, seed, d_tok_off, d_tok_len, batch, Tmax, st);
@@ -859,7 +879,7 @@ Result* run_inference(Voice& v, const int64_t* ids, const int64_t* lengths, int 
       const ConvFlowW& cf = dv.cflows[f];
       launch_convflow_pre(z, c0, cf.pre_w, cf.pre_b, hc, u, NT, Fd, st);
       R.dds(cf.dds, u, s1, t2, Fd, tok, NT);
-      R.conv(R.base_conv(cf.proj, u, Fd, pr, 32, tok, 1), tok);
+      R.row_conv(cf.proj, u, Fd, pr, 32);
       launch_rqs_inverse(z, c0 ^ 1, pr, 32, inv_sqrt, NT, st);
     }
     c0 ^= 1;  // final Flip, then ElementwiseAffine^-1; logw = logical channel 0

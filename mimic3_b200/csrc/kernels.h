@@ -47,6 +47,26 @@ struct ConvParams {
 
 void launch_conv(const ConvParams& p, int n_seg, int max_seg_len, cudaStream_t st);
 
+// Token-level fp32 conv-as-GEMM over PACKED rows (tiles span utterance boundaries, so short
+// utterances waste nothing).  rowinfo[r] = (seg_lo, seg_hi, seg_id, 0): taps outside [lo, hi) read 0.
+struct RowConvParams {
+  const float* in = nullptr;
+  int in_stride = 0, Cin = 0;
+  const float* W = nullptr;  // [taps][Cin][Cout]
+  int Cout = 0, taps = 1, pad_left = 0;
+  const float* bias = nullptr;
+  const float* ubias = nullptr;  // [n_seg][ub_stride]
+  int ub_stride = 0;
+  int act = 0;  // 0 none, 1 relu
+  float* out = nullptr;
+  int out_stride = 0;
+  const int4* rowinfo = nullptr;
+  int rows = 0;
+};
+void launch_row_conv(const RowConvParams& p, cudaStream_t st);
+void launch_fill_rowinfo(int4* rowinfo, const int* seg_off, const int* seg_len, int n_seg, int max_len,
+                         cudaStream_t st);
+
 // Fused tensor-core MRF stage (kernels_tc.cu).  Weights: 16-bit, per conv [tap][Cin/8][Cout][8].
 struct MrfParams {
   const float* x = nullptr;  // [rows][C] fp32, channels-last
@@ -64,6 +84,7 @@ struct MrfParams {
   int H = 0, HX = 0, HY = 0;
   int wg = 1;      // taps per weight-staging group (launcher)
   float inv_nk = 1.f;
+  int dbg = 0;     // M3B200_MRF_DEBUG bit mask (performance experiments only; breaks results)
 };
 // Generic tensor-core Conv1d / polyphase ConvTranspose1d (kernels_tc.cu).
 // Weights: 16-bit, [chunk][tap][K/8][NC][8] (one contiguous block per (chunk, tap): a bulk copy).

@@ -207,6 +207,144 @@ void launch_conv(const ConvParams& p, int n_seg, int max_seg_len, cudaStream_t s
 }
 
 // -------------------------------------------------------------------------------------
+// Token-level conv-as-GEMM over packed rows: 128x64 tile, 8x4 outputs per thread, BK = 16,
+// register-prefetch double buffering (global loads of tile k+1 overlap the FMAs of tile k).
+// fp32 FFMA on purpose: this feeds the duration predictor (SURVEY.md hard part 2).
+// -------------------------------------------------------------------------------------
+constexpr int RB_M = 128, RB_N = 64, RB_K = 16;
+
+__global__ void fill_rowinfo_kernel(int4* rowinfo, const int* seg_off, const int* seg_len) {
+  const int seg = blockIdx.y;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int len = seg_len[seg];
+  if (t >= len) return;
+  const int lo = seg_off[seg];
+  rowinfo[lo + t] = make_int4(lo, lo + len, seg, 0);
+}
+
+void launch_fill_rowinfo(int4* rowinfo, const int* seg_off, const int* seg_len, int n_seg, int max_len,
+                         cudaStream_t st) {
+  if (max_len <= 0) return;
+  fill_rowinfo_kernel<<<dim3((max_len + 127) / 128, n_seg), 128, 0, st>>>(rowinfo, seg_off, seg_len);
+  M3_LAUNCHED();
+}
+
+__global__ void __launch_bounds__(256, 2) row_conv_kernel(RowConvParams p) {
+  __shared__ __align__(16) float As[RB_K][RB_M + 4];
+  __shared__ __align__(16) float Bs[RB_K][RB_N];
+  const int r0 = blockIdx.x * RB_M, n0 = blockIdx.y * RB_N;
+  const int tid = threadIdx.x;
+  const int ty = tid >> 4, tx = tid & 15;  // 16 x 16 threads: rows ty*8.., cols tx*4..
+  // A loader: 128 rows x 16 k = 512 float4 -> 2 per thread (row = idx>>2, kq = idx&3)
+  const int a_row0 = tid >> 2, a_kq = tid & 3;
+  // B loader: 16 k x 64 n = 256 float4 -> 1 per thread
+  const int b_k = tid >> 4, b_n = (tid & 15) * 4;
+  const bool vecB = (p.Cout & 3) == 0;
+
+  int4 ri[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int r = r0 + a_row0 + h * 64;
+    ri[h] = r < p.rows ? p.rowinfo[r] : make_int4(0, 0, 0, 0);
+  }
+  const int ksteps = (p.Cin + RB_K - 1) / RB_K;
+  const int total = p.taps * ksteps;
+
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  float4 pa[2], pb;
+  auto fetch = [&](int it) {
+    const int tap = it / ksteps, k0 = (it - tap * ksteps) * RB_K;
+    const int shift = tap - p.pad_left;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int r = r0 + a_row0 + h * 64 + shift;
+      const int kc = k0 + a_kq * 4;
+      pa[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r >= ri[h].x && r < ri[h].y && kc < p.Cin)  // Cin % 4 == 0 (checked on the host)
+        pa[h] = *reinterpret_cast<const float4*>(p.in + (long long)r * p.in_stride + kc);
+    }
+    const int kk = k0 + b_k;
+    pb = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (kk < p.Cin) {
+      const float* wrow = p.W + ((long long)tap * p.Cin + kk) * p.Cout;
+      const int n = n0 + b_n;
+      if (vecB && n + 3 < p.Cout) pb = *reinterpret_cast<const float4*>(wrow + n);
+      else {
+        if (n + 0 < p.Cout) pb.x = wrow[n + 0];
+        if (n + 1 < p.Cout) pb.y = wrow[n + 1];
+        if (n + 2 < p.Cout) pb.z = wrow[n + 2];
+        if (n + 3 < p.Cout) pb.w = wrow[n + 3];
+      }
+    }
+  };
+  auto stash = [&]() {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int m = a_row0 + h * 64;
+      As[a_kq * 4 + 0][m] = pa[h].x;
+      As[a_kq * 4 + 1][m] = pa[h].y;
+      As[a_kq * 4 + 2][m] = pa[h].z;
+      As[a_kq * 4 + 3][m] = pa[h].w;
+    }
+    *reinterpret_cast<float4*>(&Bs[b_k][b_n]) = pb;
+  };
+
+  fetch(0);
+  stash();
+  __syncthreads();
+  for (int it = 0; it < total; ++it) {
+    if (it + 1 < total) fetch(it + 1);
+#pragma unroll
+    for (int k = 0; k < RB_K; ++k) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[k][ty * 8]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[k][ty * 8 + 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float ar[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float br[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+    }
+    __syncthreads();
+    if (it + 1 < total) {
+      stash();
+      __syncthreads();
+    }
+  }
+
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = r0 + ty * 8 + i;
+    if (r >= p.rows) continue;
+    const int seg = p.ubias ? p.rowinfo[r].z : 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= p.Cout) continue;
+      float v = acc[i][j];
+      if (p.bias) v += p.bias[n];
+      if (p.ubias) v += p.ubias[(long long)seg * p.ub_stride + n];
+      if (p.act == 1) v = fmaxf(v, 0.f);
+      p.out[(long long)r * p.out_stride + n] = v;
+    }
+  }
+}
+
+void launch_row_conv(const RowConvParams& p, cudaStream_t st) {
+  if (p.rows <= 0) return;
+  if ((p.Cin & 3) || (p.in_stride & 3)) throw std::runtime_error("row_conv: Cin and in_stride must be multiples of 4");
+  dim3 grid((p.rows + RB_M - 1) / RB_M, (p.Cout + RB_N - 1) / RB_N);
+  row_conv_kernel<<<grid, 256, 0, st>>>(p);
+  M3_LAUNCHED();
+}
+
+// -------------------------------------------------------------------------------------
 // LayerNorm over channels (modules.LayerNorm [EXT]: biased variance, eps 1e-5).
 // -------------------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {

@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) mrf_tc_kernel(MrfParams p) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (inside) t = *reinterpret_cast<const float4*>(xg + (base + g) * C + col + e * 4);
+        if (inside && !(p.dbg & 8)) t = *reinterpret_cast<const float4*>(xg + (base + g) * C + col + e * 4);
         xr[m][cc][e * 4 + 0] = t.x;
         xr[m][cc][e * 4 + 1] = t.y;
         xr[m][cc][e * 4 + 2] = t.z;
@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) mrf_tc_kernel(MrfParams p) {
           const int rr = idx / CH, c8 = idx - rr * CH;
           dsti[u] = c8 * ROWSX + rr;
           const int g = w0 - p.HX + rr;
-          if (g >= 0 && g < L) {
+          if (g >= 0 && g < L && !(p.dbg & 8)) {
             const float* src = xg + (base + g) * C + c8 * 8;
             a[u] = *reinterpret_cast<const float4*>(src);
             b[u] = *reinterpret_cast<const float4*>(src + 4);
@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) mrf_tc_kernel(MrfParams p) {
     {
       const float* b0 = sbias[j];  // warp-uniform addresses: broadcast LDS, no global latency
 #pragma unroll
-      for (int m = 0; m < NT; ++m) {
+      for (int m = 0; m < ((p.dbg & 16) ? 0 : NT); ++m) {
 #pragma unroll
         for (int cc = 0; cc < NCC; ++cc) {
           const int col = hhalf * HC + cc * 16;
@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) mrf_tc_kernel(MrfParams p) {
           // accumulators: a dependent accumulate chain costs ~115 cycles per instruction (measured,
           // tools/ubench.py), NT independent chains bring it down to ~115/NT.
 #pragma unroll 1
-          for (int t = 0; t < ntap; ++t) {
+          for (int t = 0; t < ((p.dbg & 1) ? 0 : ntap); ++t) {
             const int shift = halo_in + (g0 + t - half) * dil;
 #pragma unroll
             for (int ks = 0; ks < C / 16; ++ks) {
@@ -245,6 +245,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) mrf_tc_kernel(MrfParams p) {
           const int r = m * 128 + q * 32 + lane;
           const int g = w0 + r;
           const bool inside = g >= 0 && g < L;
+          if (p.dbg & 2) continue;
           float v[NCC][16];
 #pragma unroll
           for (int cc = 0; cc < NCC; ++cc) tc::tmem_ld16(lane_base + T0 + m * C + hhalf * HC + cc * 16, v[cc]);
@@ -275,6 +276,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) mrf_tc_kernel(MrfParams p) {
           const int r = m * 128 + q * 32 + lane;
           const int g = w0 + r;
           const bool store = r >= p.H && r < R - p.H && g < L;
+          if (p.dbg & 4) continue;
 #pragma unroll
           for (int cc = 0; cc < NCC; ++cc) {
             const int col = hhalf * HC + cc * 16;
@@ -345,6 +347,8 @@ bool mrf_tc_supported(int C, int nk, int nd, const int* k, int max_halo) {
 
 void launch_mrf_tc(const MrfParams& p, int C, int fmt, int n_seg, int max_len, cudaStream_t st) {
   MrfParams q = p;
+  static const int dbg = [] { const char* e = getenv("M3B200_MRF_DEBUG"); return e ? atoi(e) : 0; }();
+  q.dbg = dbg;
   auto pick_wg = [&](int bytes_budget) {
     int kmax = 1;
     for (int j = 0; j < p.nk; ++j) kmax = max(kmax, p.k[j]);
