@@ -224,15 +224,11 @@ def main():
     if distributed:
         # NCCL scatter of the padded id tensor from rank 0 (north_star: the only collectives on the
         # path are the id scatter and the PCM gather)
-        chunks = None
-        if rank == 0:
-            full = torch.from_numpy(ids).cuda()
-            chunks = [full[r * per:(r + 1) * per if r < world - 1 else GB].contiguous() for r in range(world)]
-        d_ids = torch.empty((hi - lo, IDS_PER_UTT), dtype=torch.int64, device="cuda")
-        if all(c.shape == d_ids.shape for c in (chunks or [d_ids])):
-            dist.scatter(d_ids, chunks, src=0)
-        else:  # ragged last shard
-            d_ids.copy_(torch.from_numpy(ids[lo:hi]))
+        from mimic3_b200.shard import gather_pcm, scatter_ids, shard_bounds
+        lo, hi = shard_bounds(GB, world, rank)
+        d_ids, d_len, d_sid = scatter_ids(ids if rank == 0 else None, lengths if rank == 0 else None,
+                                          sid if rank == 0 else None, torch.device("cuda", local_rank))
+        my_lengths, my_sid = d_len.cpu().numpy(), d_sid.cpu().numpy()
     else:
         d_ids = torch.from_numpy(ids[lo:hi]).cuda()
     h_ids = np.ascontiguousarray(ids[lo:hi])
@@ -242,8 +238,26 @@ def main():
         return sess.infer(IDS_PER_UTT, my_lengths, scales, my_sid, seed=seed, host_copy=False,
                           device_ids_ptr=d_ids.data_ptr(), stage_timing=timing)
 
+    pcm_dev = torch.empty(1, dtype=torch.int16, device="cuda")
+
     def step_e2e(seed):
-        return sess.infer(h_ids, my_lengths, scales, my_sid, seed=seed)
+        """Host ids in, int16 PCM back on the host.  N>1: rank 0 owns the host buffers; ids are
+        scattered and PCM gathered over NCCL, then rank 0 copies to (pinned) host memory."""
+        nonlocal pcm_dev
+        if not distributed:
+            return sess.infer(h_ids, my_lengths, scales, my_sid, seed=seed).total_samples
+        di, dl, ds = scatter_ids(ids if rank == 0 else None, lengths if rank == 0 else None,
+                                 sid if rank == 0 else None, torch.device("cuda", local_rank))
+        cap = int(dl.sum().item()) * 64 * sess.info.hop_length  # generous bound on samples
+        if pcm_dev.numel() < cap:
+            pcm_dev = torch.empty(cap, dtype=torch.int16, device="cuda")
+        r = sess.infer(IDS_PER_UTT, dl.cpu().numpy(), scales, ds.cpu().numpy(), seed=seed, host_copy=False,
+                       device_ids_ptr=di.data_ptr(), device_pcm_out=pcm_dev)
+        out = gather_pcm(pcm_dev[: r.total_samples], r.sample_offsets, torch.device("cuda", local_rank))
+        if rank == 0:
+            host = [b.cpu() for b in out[0]]
+            return sum(int(h.numel()) for h in host)
+        return 0
 
     def sync_all():
         torch.cuda.synchronize()
@@ -292,13 +306,14 @@ def main():
     t1 = time.perf_counter()
     e2e_samples = 0
     for k in range(args.steps):
-        r = step_e2e(2000 + k)
-        e2e_samples += r.total_samples
+        e2e_samples += step_e2e(2000 + k)
     sync_all()
     e2e_wall = time.perf_counter() - t1
 
     # ---- reduce over ranks: max time, summed samples ------------------------------------------------
     vec = torch.tensor([wall, dev_ms / 1e3, e2e_wall], dtype=torch.float64, device="cuda")
+    if distributed and rank != 0:
+        e2e_samples = 0  # rank 0 already counted every gathered sample
     cnt = torch.tensor([samples, e2e_samples, launches, frames], dtype=torch.float64, device="cuda")
     if distributed:
         dist.all_reduce(vec, op=dist.ReduceOp.MAX)

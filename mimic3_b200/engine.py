@@ -158,7 +158,10 @@ class B200Session:
     def infer(self, ids: np.ndarray, lengths: np.ndarray, scales: Sequence[float],
               sid: Optional[np.ndarray] = None, seed: int = 0, keep_float: bool = False,
               debug_tensors: Sequence[str] = (), host_copy: bool = True,
-              device_ids_ptr: Optional[int] = None, stage_timing: bool = False) -> InferenceResult:
+              device_ids_ptr: Optional[int] = None, stage_timing: bool = False,
+              device_pcm_out=None) -> InferenceResult:
+        """``device_pcm_out``: optional torch int16 CUDA tensor; the packed PCM is copied into it on the
+        device (for NCCL gathers) before the engine's buffers are released."""
         lengths = np.ascontiguousarray(lengths, dtype=np.int64)
         batch = int(lengths.shape[0])
         flags = 0
@@ -208,6 +211,14 @@ class B200Session:
             out.device_ms = float(self._lib.m3_result_device_ms(res))
             out.launches = int(self._lib.m3_result_kernel_launches(res))
             out.device_pcm_ptr = self._lib.m3_result_device_pcm(res)
+            if device_pcm_out is not None and total:
+                import torch
+
+                class _View:  # zero-copy view of the engine's device buffer
+                    __cuda_array_interface__ = {"shape": (total,), "typestr": "<i2",
+                                                "data": (int(out.device_pcm_ptr), True), "version": 2}
+                device_pcm_out[:total].copy_(torch.as_tensor(_View(), device=device_pcm_out.device))
+                torch.cuda.current_stream(device_pcm_out.device).synchronize()
             out.tensors = {}
             for name in debug_tensors:
                 data = C.POINTER(C.c_float)()
