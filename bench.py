@@ -245,7 +245,11 @@ def main():
         scattered and PCM gathered over NCCL, then rank 0 copies to (pinned) host memory."""
         nonlocal pcm_dev
         if not distributed:
-            return sess.infer(h_ids, my_lengths, scales, my_sid, seed=seed).total_samples
+            r = sess.infer(h_ids, my_lengths, scales, my_sid, seed=seed, copy=False)  # PCM lands in pinned host memory
+            n = r.total_samples
+            assert r.pcm.shape[0] == n
+            r.close()
+            return n
         di, dl, ds = scatter_ids(ids if rank == 0 else None, lengths if rank == 0 else None,
                                  sid if rank == 0 else None, torch.device("cuda", local_rank))
         cap = int(dl.sum().item()) * 64 * sess.info.hop_length  # generous bound on samples

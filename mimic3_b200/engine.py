@@ -110,10 +110,35 @@ def _raise(lib, code: int):
 
 
 class InferenceResult:
-    """Outputs of one engine call (all arrays are owned copies)."""
+    """Outputs of one engine call.  By default ``pcm`` / ``audio`` are owned copies.  With
+    ``infer(..., copy=False)`` they are zero-copy views of the engine's pinned host buffers, valid
+    until ``close()`` (which turns them into copies and returns the buffers to the engine's pool)."""
 
     __slots__ = ("pcm", "audio", "sample_offsets", "frames", "peaks", "device_ms", "launches",
-                 "tensors", "device_pcm_ptr")
+                 "tensors", "device_pcm_ptr", "_lib", "_res")
+
+    def detach(self):
+        """Turn the views into owned copies and release the engine buffers."""
+        res, self._res = getattr(self, "_res", None), None
+        if res:
+            self.pcm = None if self.pcm is None else self.pcm.copy()
+            self.audio = None if self.audio is None else self.audio.copy()
+            self._lib.m3_result_free(res)
+
+    def close(self):
+        """Release the engine buffers; zero-copy views become invalid and are dropped."""
+        res, self._res = getattr(self, "_res", None), None
+        if res:
+            self.pcm = self.audio = None
+            self._lib.m3_result_free(res)
+
+    def __del__(self):  # pragma: no cover
+        res, self._res = getattr(self, "_res", None), None
+        if res:
+            try:
+                self._lib.m3_result_free(res)
+            except Exception:
+                pass
 
     def utterance_pcm(self, b: int) -> np.ndarray:
         return self.pcm[self.sample_offsets[b]:self.sample_offsets[b + 1]]
@@ -159,7 +184,7 @@ class B200Session:
               sid: Optional[np.ndarray] = None, seed: int = 0, keep_float: bool = False,
               debug_tensors: Sequence[str] = (), host_copy: bool = True,
               device_ids_ptr: Optional[int] = None, stage_timing: bool = False,
-              device_pcm_out=None) -> InferenceResult:
+              device_pcm_out=None, copy: bool = True) -> InferenceResult:
         """``device_pcm_out``: optional torch int16 CUDA tensor; the packed PCM is copied into it on the
         device (for NCCL gathers) before the engine's buffers are released."""
         lengths = np.ascontiguousarray(lengths, dtype=np.int64)
@@ -196,8 +221,9 @@ class B200Session:
                                 t_stride, sc, sid_p, C.c_uint64(seed & (2 ** 64 - 1)), flags, C.byref(res))
         if rc != M3_OK:
             _raise(self._lib, rc)
-        try:
-            out = InferenceResult()
+        out = InferenceResult()
+        out._lib, out._res = self._lib, res
+        if True:
             off = np.ctypeslib.as_array(self._lib.m3_result_sample_offsets(res), (batch + 1,)).copy()
             out.sample_offsets = off
             out.frames = np.ctypeslib.as_array(self._lib.m3_result_num_frames(res), (batch,)).copy()
@@ -205,9 +231,9 @@ class B200Session:
             total = int(off[-1])
             out.pcm = out.audio = None
             if host_copy:
-                out.pcm = np.ctypeslib.as_array(self._lib.m3_result_pcm(res), (max(total, 1),))[:total].copy()
+                out.pcm = np.ctypeslib.as_array(self._lib.m3_result_pcm(res), (max(total, 1),))[:total]
                 if keep_float:
-                    out.audio = np.ctypeslib.as_array(self._lib.m3_result_audio(res), (max(total, 1),))[:total].copy()
+                    out.audio = np.ctypeslib.as_array(self._lib.m3_result_audio(res), (max(total, 1),))[:total]
             out.device_ms = float(self._lib.m3_result_device_ms(res))
             out.launches = int(self._lib.m3_result_kernel_launches(res))
             out.device_pcm_ptr = self._lib.m3_result_device_pcm(res)
@@ -227,9 +253,9 @@ class B200Session:
                 if rc == M3_OK:
                     n = rows.value * cols.value
                     out.tensors[name] = np.ctypeslib.as_array(data, (max(n, 1),))[:n].copy().reshape(rows.value, cols.value)
+            if copy or not host_copy:
+                out.detach()  # owned copies (or nothing on the host): give the context back immediately
             return out
-        finally:
-            self._lib.m3_result_free(res)
 
     # -- onnxruntime-compatible call (voice.py:230) ---------------------------------------
     def run(self, output_names, input_feed: Dict[str, np.ndarray], run_options=None) -> List[np.ndarray]:
