@@ -242,3 +242,45 @@ def test_tensor_core_mrf_matches_oracle_and_simt(voices, built_library, oracles,
             assert rms <= (RMS_TOL if fmt == "fp16" else 5 * RMS_TOL), (fmt, b, rms)  # fp16 is the shipped default
         sess.close()
     simt.close()
+
+
+def test_long_form_cfg4_shape(sessions, oracles):
+    """BASELINE configs[3]: long-form utterances (~1800 ids), length_scale in {0.8, 1.0, 1.2}.
+    Parity vs the oracle at 600 ids (seconds on CPU); properties at the full 1800."""
+    sess, orc = sessions("low"), oracles("low")
+    rng = np.random.default_rng(31)
+    ids, lens = _batch(rng, sess.info.num_symbols, [600])
+    worst = _compare(sess, orc, ids, lens, (0.0, 1.2, 0.0), None)
+    print(f"long-form 600 ids: worst RMS {worst:.3e}")
+    ids, lens = _batch(rng, sess.info.num_symbols, [1800, 1750, 900, 1800])
+    frames = {}
+    for ls in (0.8, 1.0, 1.2):
+        r = sess.infer(ids, lens, (0.0, ls, 0.0), None, keep_float=True)
+        frames[ls] = r.frames.copy()
+        assert np.isfinite(r.audio).all() and np.abs(r.audio).max() <= 1.0
+        assert np.all(np.diff(r.sample_offsets) == r.frames * sess.info.hop_length)
+        one = sess.infer(ids[2:3, :900], lens[2:3], (0.0, ls, 0.0), None)       # row 2 alone == row 2 in the batch
+        np.testing.assert_array_equal(one.pcm, r.utterance_pcm(2))
+    assert np.all(frames[0.8] <= frames[1.0]) and np.all(frames[1.0] <= frames[1.2])
+
+
+def test_mixed_voice_residency_cfg5(voices, built_library):
+    """BASELINE configs[4]: several voices resident at once, rows grouped by voice; switching voice is
+    a pointer swap and must not disturb results."""
+    from mimic3_b200.engine import B200Session
+    names = ["low_ms", "low", "tiny_ms"]
+    sess = {n: B200Session(str(voices(n))) for n in names}
+    rng = np.random.default_rng(41)
+    jobs = {}
+    for n in names:
+        ns = sess[n].info.num_symbols
+        ids, lens = _batch(rng, ns, [int(rng.integers(10, 60)) for _ in range(5)])
+        sid = (np.arange(5) % sess[n].info.n_speakers) if sess[n].info.has_speaker_embedding else None
+        jobs[n] = (ids, lens, sid)
+    first = {n: sess[n].infer(*jobs[n][:2], (0.0, 1.0, 0.0), jobs[n][2]).pcm for n in names}
+    for _ in range(2):  # interleave voices
+        for n in reversed(names):
+            again = sess[n].infer(*jobs[n][:2], (0.0, 1.0, 0.0), jobs[n][2]).pcm
+            np.testing.assert_array_equal(again, first[n])
+    for s in sess.values():
+        s.close()
