@@ -242,7 +242,7 @@ class B200Session:
 
                 class _View:  # zero-copy view of the engine's device buffer
                     __cuda_array_interface__ = {"shape": (total,), "typestr": "<i2",
-                                                "data": (int(out.device_pcm_ptr), True), "version": 2}
+                                                "data": (int(out.device_pcm_ptr), False), "version": 2}
                 device_pcm_out[:total].copy_(torch.as_tensor(_View(), device=device_pcm_out.device))
                 torch.cuda.current_stream(device_pcm_out.device).synchronize()
             out.tensors = {}
