@@ -395,6 +395,73 @@ std::unique_ptr<DeviceVoice> build_device_voice(const HostVoice& hv, int device)
     }
   }
 
+  // ---- fused coupling-layer packing (tensor cores): weights in the kernel's schedule order
+  {
+    const int Hf = dv.flow_hidden, nl = dv.flow_layers, half = I / 2;
+    const int nfl = int(dv.couplings.size());
+    if (flow_tc_supported(Hf, half, nl, dv.flow_kernel)) {
+      for (int a = 0; a < nfl; ++a) {  // a = application order; module = flows.{2*(nfl-1-a)}
+        CouplingW& cw = dv.couplings[a];
+        const std::string p = "flow.flows." + std::to_string(2 * (nfl - 1 - a));
+        const bool rev = ((a + 1) & 1) != 0;  // odd number of Flips so far: halves swapped and reversed
+        cw.ftc.x0_coff = rev ? half : 0;
+        cw.ftc.x1_coff = rev ? 0 : half;
+        auto perm = [&](int ch) { return rev ? half - 1 - ch : ch; };
+        while (B.h16.size() % 64) B.h16.push_back(0);
+        cw.ftc.woff = B.h16.size();
+        auto stage = [&](int K, auto&& wfun) {  // wfun(k, j) -> weight of input k, stage column j
+          const size_t o = B.h16.size();
+          B.h16.resize(o + size_t(K) * 64, 0);
+          for (int k = 0; k < K; ++k)
+            for (int j = 0; j < 64; ++j) B.h16[o + (size_t(k / 8) * 64 + j) * 8 + (k & 7)] = B.cvt16(wfun(k, j));
+        };
+        const OnnxTensor& wpre = hv.need(p + ".pre.weight", {Hf, half, 1});
+        const OnnxTensor& bpre = hv.need(p + ".pre.bias", {Hf});
+        for (int cc = 0; cc < Hf / 64; ++cc)
+          stage(half, [&](int k, int j) { return wpre.f32[size_t(64 * cc + j) * half + perm(k)]; });
+        std::vector<float> inb(size_t(nl) * 2 * Hf), cumb(size_t(nl) * Hf), skb(Hf, 0.f), pob(half);
+        std::vector<float> run(bpre.f32.begin(), bpre.f32.end());
+        for (int i = 0; i < nl; ++i) {
+          const std::string is = std::to_string(i);
+          const OnnxTensor& win = hv.need(p + ".enc.in_layers." + is + ".weight", {2 * Hf, Hf, dv.flow_kernel});
+          const OnnxTensor& bin = hv.need(p + ".enc.in_layers." + is + ".bias", {2 * Hf});
+          const int rsn = i < nl - 1 ? 2 * Hf : Hf;
+          const OnnxTensor& wrs = hv.need(p + ".enc.res_skip_layers." + is + ".weight", {rsn, Hf, 1});
+          const OnnxTensor& brs = hv.need(p + ".enc.res_skip_layers." + is + ".bias", {rsn});
+          for (int n = 0; n < 2 * Hf; ++n) inb[size_t(i) * 2 * Hf + n] = bin.f32[n];
+          for (int n = 0; n < Hf; ++n) cumb[size_t(i) * Hf + n] = run[n];
+          for (int cc = 0; cc < Hf / 32; ++cc)
+            for (int tap = 0; tap < dv.flow_kernel; ++tap)
+              stage(Hf, [&](int k, int j) {
+                const int ch = (j < 32 ? 0 : Hf) + 32 * cc + (j & 31);
+                return win.f32[(size_t(ch) * Hf + k) * dv.flow_kernel + tap];
+              });
+          for (int cc = 0; cc < rsn / 64; ++cc)
+            stage(Hf, [&](int k, int j) { return wrs.f32[size_t(64 * cc + j) * Hf + k]; });
+          if (i < nl - 1) {
+            for (int n = 0; n < Hf; ++n) run[n] += brs.f32[n];
+            for (int n = 0; n < Hf; ++n) skb[n] += brs.f32[Hf + n];
+          } else {
+            for (int n = 0; n < Hf; ++n) skb[n] += brs.f32[n];
+          }
+        }
+        const OnnxTensor& wpo = hv.need(p + ".post.weight", {half, Hf, 1});
+        const OnnxTensor& bpo = hv.need(p + ".post.bias", {half});
+        for (int cc = 0; cc < (half + 63) / 64; ++cc)
+          stage(Hf, [&](int k, int j) {
+            const int n = 64 * cc + j;
+            return n < half ? wpo.f32[size_t(perm(n)) * Hf + k] : 0.f;
+          });
+        for (int n = 0; n < half; ++n) pob[n] = bpo.f32[perm(n)];
+        B.place(&cw.ftc.in_bias, inb);
+        B.place(&cw.ftc.cum_bias, cumb);
+        B.place(&cw.ftc.skip_bias, skb);
+        B.place(&cw.ftc.post_bias, pob);
+        cw.ftc.ok = true;
+      }
+    }
+  }
+
   // ---- HiFi-GAN decoder
   {
     const int C0 = c.up_init;
@@ -980,7 +1047,31 @@ Result* run_inference(Voice& v, const int64_t* ids, const int64_t* lengths, int 
     float* act = A2.alloc<float>(size_t(NF) * Hf);
     float* skip = A2.alloc<float>(size_t(NF) * Hf);
     const int half = I / 2;
-    for (size_t f = 0; f < dv.couplings.size(); ++f) {
+    const bool fused = dv.use_tc && !dv.couplings.empty() && dv.couplings[0].ftc.ok && !getenv("M3B200_UNFUSED_FLOW");
+    for (size_t f = 0; fused && f < dv.couplings.size(); ++f) {
+      const CouplingW& cw = dv.couplings[f];
+      FlowTcParams fp;
+      fp.z = z;
+      fp.z_stride = I;
+      fp.x0_coff = cw.ftc.x0_coff;
+      fp.x1_coff = cw.ftc.x1_coff;
+      fp.Hc = Hf;
+      fp.half = half;
+      fp.nl = dv.flow_layers;
+      fp.w = dv.slab16 + cw.ftc.woff;
+      fp.in_bias = cw.ftc.in_bias;
+      fp.cum_bias = cw.ftc.cum_bias;
+      fp.skip_bias = cw.ftc.skip_bias;
+      fp.post_bias = cw.ftc.post_bias;
+      if (const float* ub = ubias(cw.cond_off)) {
+        fp.cond = ub;
+        fp.cond_stride = dv.n_cond;
+      }
+      fp.seg_off = d_frm_off;
+      fp.seg_len = d_frm_len;
+      launch_flow_tc(fp, dv.tc_fmt, batch, Fmax, st);
+    }
+    for (size_t f = 0; !fused && f < dv.couplings.size(); ++f) {
       const CouplingW& cw = dv.couplings[f];
       launch_flip_channels(z, int(NF), I, st);
       if (R.tc_ok(cw.pre.tc)) R.tc_conv(R.base_tc(cw.pre.tc, cw.pre.b, z, I, h, Hf, frm, 1), frm);

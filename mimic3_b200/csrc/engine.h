@@ -57,10 +57,18 @@ struct ConvFlowW {
   Lin proj;
 };
 
+struct FlowTcW {  // fused coupling-layer packing (kernels_tc_flow.cu)
+  bool ok = false;
+  unsigned long long woff = 0;
+  const float *in_bias = nullptr, *cum_bias = nullptr, *skip_bias = nullptr, *post_bias = nullptr;
+  int x0_coff = 0, x1_coff = 0;
+};
+
 struct CouplingW {
   Lin pre, post;
   std::vector<Lin> in, rs;
   int cond_off = -1;
+  FlowTcW ftc;
 };
 
 struct UpW {

@@ -112,6 +112,26 @@ struct TcConvParams {
 bool conv_tc_supported(int K, int NC, int taps, int dil);
 void launch_conv_tc(const TcConvParams& p, int fmt, int n_seg, int max_seg_len, cudaStream_t st);
 
+// Fused coupling layer of the flow (kernels_tc_flow.cu).  Weights: one 16-bit stream in schedule order
+// (pre chunks | per layer: gate chunks x 5 taps, res chunks, skip chunks | post chunks), each stage
+// [K/8][64][8]; the channel Flip is folded into pre/post packing and x0_coff / x1_coff.
+struct FlowTcParams {
+  float* z = nullptr;  // [frames][z_stride] fp32, updated in place (x1 half)
+  int z_stride = 0, x0_coff = 0, x1_coff = 0;
+  int Hc = 0, half = 0, nl = 0;
+  const uint16_t* w = nullptr;
+  const float* in_bias = nullptr;    // [nl][2*Hc]
+  const float* cum_bias = nullptr;   // [nl][Hc]: b_pre + sum_{j<i} b_res_j
+  const float* skip_bias = nullptr;  // [Hc]
+  const float* post_bias = nullptr;  // [half] (flip-permuted)
+  const float* cond = nullptr;       // per utterance [cond_stride], laid out like in_bias; may be null
+  int cond_stride = 0;
+  const int* seg_off = nullptr;
+  const int* seg_len = nullptr;
+};
+bool flow_tc_supported(int Hc, int half, int nl, int kernel);
+void launch_flow_tc(const FlowTcParams& p, int fmt, int n_seg, int max_len, cudaStream_t st);
+
 bool mrf_tc_supported(int C, int nk, int nd, const int* k, int max_halo);
 // fmt: 0 = fp16 operands, 1 = bf16 operands
 void launch_mrf_tc(const MrfParams& p, int C, int fmt, int n_seg, int max_len, cudaStream_t st);
