@@ -350,7 +350,7 @@ bool flow_tc_supported(int Hc, int half, int nl, int kernel) {
   if (Hc % 64 || half % 16 || half > Hc) return false;
   if (2 * Hc + 2 * FL_NC > 512) return false;  // TMEM: H + SKIP + two accumulators
   if (128 - 4 * nl < 32) return false;
-  return flow_tc_smem_bytes(Hc, half, nl) <= size_t(227 * 1024);
+  return flow_tc_smem_bytes(Hc, half, nl) <= size_t(225 * 1024);
 }
 
 void launch_flow_tc(const FlowTcParams& p, int fmt, int n_seg, int max_len, cudaStream_t st) {
@@ -358,8 +358,8 @@ void launch_flow_tc(const FlowTcParams& p, int fmt, int n_seg, int max_len, cuda
   const size_t smem = flow_tc_smem_bytes(p.Hc, p.half, p.nl);
   static thread_local bool configured[2] = {false, false};
   if (!configured[fmt ? 1 : 0]) {
-    cudaError_t e = fmt ? cudaFuncSetAttribute(flow_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)
-                        : cudaFuncSetAttribute(flow_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = fmt ? cudaFuncSetAttribute(flow_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024)
+                        : cudaFuncSetAttribute(flow_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
     if (e != cudaSuccess) throw std::runtime_error("flow_tc: cannot reserve shared memory");
     configured[fmt ? 1 : 0] = true;
   }
