@@ -586,6 +586,40 @@ std::unique_ptr<DeviceVoice> build_device_voice(const HostVoice& hv, int device)
     }
   }
 
+  // ---- fused last stage (ConvTranspose + MRF + conv_post): extra operand packings
+  if (!c.up_rates.empty() && !dv.mrf.empty()) {
+    const size_t li = c.up_rates.size() - 1;
+    const UpW& u = dv.ups[li];
+    const MrfStageW& ms = dv.mrf[li];
+    const int C = u.cout;
+    if (ms.ok && dv.post_c == C && dv.post_k == 7 &&
+        dec_last_supported(C, u.cin, u.k, u.u, ms.nk, ms.nd, ms.HX, ms.HY)) {
+      const OnnxTensor& w = hv.need("dec.ups." + std::to_string(li) + ".weight", {u.cin, u.cout, u.k});
+      while (B.h16.size() % 64) B.h16.push_back(0);
+      dv.dec_last.up_woff = B.h16.size();
+      {  // conv over the zero-stuffed input: W'[jj][ci][co] = w[ci][co][k-1-jj], layout [jj][cin/8][C][8]
+        const size_t o = B.h16.size();
+        B.h16.resize(o + size_t(u.k) * u.cin * C, 0);
+        for (int jj = 0; jj < u.k; ++jj)
+          for (int ci = 0; ci < u.cin; ++ci)
+            for (int co = 0; co < C; ++co)
+              B.h16[o + ((size_t(jj) * (u.cin / 8) + ci / 8) * C + co) * 8 + (ci & 7)] =
+                  B.cvt16(w.f32[(size_t(ci) * u.cout + co) * u.k + (u.k - 1 - jj)]);
+      }
+      const OnnxTensor& pw = hv.need("dec.conv_post.weight", {1, C, 7});
+      while (B.h16.size() % 64) B.h16.push_back(0);
+      dv.dec_last.post_woff = B.h16.size();
+      {  // [tap][C/8][16][8], output column 0 is the real one
+        const size_t o = B.h16.size();
+        B.h16.resize(o + size_t(7) * C * 16, 0);
+        for (int tap = 0; tap < 7; ++tap)
+          for (int ci = 0; ci < C; ++ci)
+            B.h16[o + ((size_t(tap) * (C / 8) + ci / 8) * 16 + 0) * 8 + (ci & 7)] = B.cvt16(pw.f32[size_t(ci) * 7 + tap]);
+      }
+      dv.dec_last.ok = true;
+    }
+  }
+
   // ---- conditioning GEMM [G][n_cond]
   if (G && !cond_layers.empty()) {
     int n = 0;
@@ -1159,9 +1193,78 @@ Result* run_inference(Voice& v, const int64_t* ids, const int64_t* lengths, int 
   R.mark("conv_pre");
   int scale = 1;
   const int nk = int(c.rb_kernels.size());
+  const bool fuse_last = dv.use_tc && dv.dec_last.ok && !getenv("M3B200_UNFUSED_DEC");
+  float* audio = A2.alloc<float>(size_t(NF) * hop);
+  int16_t* pcm = A2.alloc<int16_t>(size_t(NF) * hop);
+  unsigned* peak = A2.alloc<unsigned>(batch);
+  M3_CUDA(cudaMemsetAsync(peak, 0, size_t(batch) * 4, st));
+  bool audio_done = false;
   for (size_t i = 0; i < dv.ups.size(); ++i) {
     const UpW& u = dv.ups[i];
     const int out_scale = scale * u.u;
+    if (fuse_last && i + 1 == dv.ups.size()) {
+      const MrfStageW& ms = dv.mrf[i];
+      DecStageParams dp;
+      dp.yprev = cur;
+      dp.cin = u.cin;
+      dp.up_u = u.u;
+      dp.prev_scale = scale;
+      dp.scale = out_scale;
+      dp.audio = audio;
+      dp.peak_bits = peak;
+      dp.w16 = dv.slab16;
+      int ns = 0;
+      DecConv up;
+      up.woff = dv.dec_last.up_woff;
+      up.K = u.cin;
+      up.N = u.cout;
+      up.taps = u.k;
+      up.dil = 1;
+      up.pad_left = u.k - 1 - u.pad;
+      up.kind = 0;
+      dp.steps[ns++] = up;
+      dp.up = up;
+      for (int j = 0; j < ms.nk; ++j) {
+        const ResBlockW& rb = dv.rbs[i * nk + j];
+        for (int d = 0; d < ms.nd; ++d) {
+          DecConv cvn;
+          cvn.woff = ms.woff[j][d];
+          cvn.K = u.cout;
+          cvn.N = u.cout;
+          cvn.taps = rb.k;
+          cvn.dil = rb.dil[d];
+          cvn.pad_left = (rb.k - 1) / 2;
+          cvn.kind = d + 1 == ms.nd ? 2 : 1;
+          cvn.rb = j;
+          dp.steps[ns++] = cvn;
+        }
+        dp.bias0[j] = rb.c1[0].b;
+      }
+      DecConv po;
+      po.woff = dv.dec_last.post_woff;
+      po.K = u.cout;
+      po.N = 16;
+      po.taps = 7;
+      po.dil = 1;
+      po.pad_left = 3;
+      po.kind = 3;
+      dp.steps[ns++] = po;
+      dp.nsteps = ns;
+      dp.up_bias = u.b;
+      dp.late_bias = ms.late_bias;
+      dp.nk = ms.nk;
+      dp.inv_nk = 1.0f / float(ms.nk);
+      dp.seg_off = d_frm_off;
+      dp.seg_len = d_frm_len;
+      dp.HX = ms.HX;
+      dp.HY = ms.HY;
+      dp.H = ms.HX + ms.HY + 3;
+      launch_dec_last(dp, u.cout, dv.tc_fmt, batch, Fmax, st);
+      R.mark("mrf");
+      scale = out_scale;
+      audio_done = true;
+      break;
+    }
     const size_t n = size_t(NF) * out_scale * u.cout;
     float* xu = A2.alloc<float>(n);
     float* yb[2] = {A2.alloc<float>(n), A2.alloc<float>(n)};
@@ -1280,11 +1383,8 @@ Result* run_inference(Voice& v, const int64_t* ids, const int64_t* lengths, int 
     scale = out_scale;
     if (R.debug) R.dump(("mrf" + std::to_string(i)).c_str(), sum, NF * out_scale, u.cout);
   }
-  float* audio = A2.alloc<float>(size_t(NF) * hop);
-  int16_t* pcm = A2.alloc<int16_t>(size_t(NF) * hop);
-  unsigned* peak = A2.alloc<unsigned>(batch);
-  M3_CUDA(cudaMemsetAsync(peak, 0, size_t(batch) * 4, st));
-  launch_conv_post(cur, dv.post_c, dv.post_w, dv.post_k, 0.01f, audio, peak, d_frm_off, d_frm_len, hop, batch, Fmax, st);
+  if (!audio_done)
+    launch_conv_post(cur, dv.post_c, dv.post_w, dv.post_k, 0.01f, audio, peak, d_frm_off, d_frm_len, hop, batch, Fmax, st);
   launch_to_int16(audio, peak, pcm, d_frm_off, d_frm_len, hop, batch, Fmax, st);
   R.mark("post_int16");
 

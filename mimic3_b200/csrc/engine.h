@@ -91,8 +91,14 @@ struct MrfStageW {  // tensor-core packing of one MRF stage (kernels_tc.cu)
   int H = 0, HX = 0, HY = 0, nk = 0, nd = 0;
 };
 
+struct DecLastW {  // fused last generator stage (kernels_tc_dec.cu)
+  bool ok = false;
+  unsigned long long up_woff = 0, post_woff = 0;
+};
+
 struct DeviceVoice {
   VoiceConfig cfg;
+  DecLastW dec_last;
   int device = 0;
   float* slab = nullptr;  // all weights, one allocation
   uint16_t* slab16 = nullptr;  // 16-bit tensor-core operands

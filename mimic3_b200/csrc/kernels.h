@@ -112,6 +112,34 @@ struct TcConvParams {
 bool conv_tc_supported(int K, int NC, int taps, int dil);
 void launch_conv_tc(const TcConvParams& p, int fmt, int n_seg, int max_seg_len, cudaStream_t st);
 
+// Fused last generator stage: ConvTranspose + MRF + conv_post/tanh/peak (kernels_tc_dec.cu).
+struct DecConv {
+  unsigned long long woff = 0;  // element offset of [tap][K/8][N][8] in w16
+  int K = 0, N = 0, taps = 1, dil = 1, pad_left = 0;
+  int kind = 0;  // 0 transposed conv (zero-stuffed input), 1 resblock conv, 2 last conv of a resblock, 3 conv_post
+  int rb = 0;    // resblock index (kinds 1, 2)
+};
+struct DecStageParams {
+  const float* yprev = nullptr;  // [rows_prev][cin] fp32: previous stage output (pre-activation)
+  int cin = 0, up_u = 1, prev_scale = 1, scale = 1;
+  float* audio = nullptr;
+  unsigned* peak_bits = nullptr;
+  const uint16_t* w16 = nullptr;
+  DecConv steps[12];
+  int nsteps = 0;
+  DecConv up;  // == steps[0]
+  const float* up_bias = nullptr;
+  const float* bias0[4] = {};
+  const float* late_bias = nullptr;
+  int nk = 0;
+  float inv_nk = 1.f;
+  const int* seg_off = nullptr;
+  const int* seg_len = nullptr;
+  int H = 0, HX = 0, HY = 0, stride = 0, wb_bytes = 16 * 1024;
+};
+bool dec_last_supported(int C, int cin, int up_k, int up_u, int nk, int nd, int HX, int HY);
+void launch_dec_last(const DecStageParams& p, int C, int fmt, int n_seg, int max_len, cudaStream_t st);
+
 // Fused coupling layer of the flow (kernels_tc_flow.cu).  Weights: one 16-bit stream in schedule order
 // (pre chunks | per layer: gate chunks x 5 taps, res chunks, skip chunks | post chunks), each stage
 // [K/8][64][8]; the channel Flip is folded into pre/post packing and x0_coff / x1_coff.

@@ -229,6 +229,9 @@ def test_tensor_core_mrf_matches_oracle_and_simt(voices, built_library, oracles,
         r = sess.infer(ids, lens, (0.0, 1.0, 0.0), sid, keep_float=True, debug_tensors=names)
         np.testing.assert_array_equal(r.frames, ref.frames)
         for name in names:
+            if name not in r.tensors:   # the fused last stage never materialises its MRF output
+                assert name == "mrf2"
+                continue
             a, b = r.tensors[name], ref.tensors[name]
             rel = np.sqrt(np.mean((a - b) ** 2)) / np.sqrt(np.mean(b ** 2))
             print(f"{fmt} {name}: relative RMS vs SIMT fp32 {rel:.3e}")
