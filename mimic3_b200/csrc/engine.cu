@@ -114,6 +114,35 @@ struct Builder {
     return *reinterpret_cast<uint16_t*>(&h);
   }
 
+  // fp16 hi/lo split packing of W[tap][k][n] for rowgemm_tc_kernel:
+  // [chunk][K block][tap][hi|lo][4][64][8]
+  void rows_pack(RowTcW& t, const std::vector<float>& W, int taps, int K, int N) {
+    t.ok = false;
+    if (!rowgemm_tc_supported(K, taps)) return;
+    const int KB = 32, NCc = 64;
+    const int chunks = (N + NCc - 1) / NCc, nkb = K / KB;
+    while (h16.size() % 64) h16.push_back(0);
+    t.woff = h16.size();
+    const size_t o = h16.size();
+    h16.resize(o + rowgemm_tc_weight_elems(K, N, taps), 0);
+    for (int c = 0; c < chunks; ++c)
+      for (int kb = 0; kb < nkb; ++kb)
+        for (int tap = 0; tap < taps; ++tap)
+          for (int kk = 0; kk < KB; ++kk)
+            for (int j = 0; j < NCc; ++j) {
+              const int n = c * NCc + j;
+              if (n >= N) continue;
+              const float w = W[(size_t(tap) * K + kb * KB + kk) * N + n];
+              const __half hi = __float2half_rn(w);
+              const __half lo = __float2half_rn((w - __half2float(hi)) * 2048.f);
+              const size_t blk = ((size_t(c) * nkb + kb) * taps + tap) * 2;
+              const size_t in_blk = (size_t(kk / 8) * NCc + j) * 8 + (kk & 7);
+              h16[o + (blk + 0) * (KB * NCc) + in_blk] = *reinterpret_cast<const uint16_t*>(&hi);
+              h16[o + (blk + 1) * (KB * NCc) + in_blk] = *reinterpret_cast<const uint16_t*>(&lo);
+            }
+    t.ok = true;
+  }
+
   // Pack logical weights W[tap][k][n] (n < Ncols) for conv_tc_kernel.  gate: the Ncols = 2*N
   // columns are (a | b) halves and every chunk carries NC/2 a-columns followed by their b-columns.
   void tc_pack(TcConvW& t, const std::vector<float>& W, int taps, int K, int N, int dil, bool gate) {
@@ -165,14 +194,16 @@ struct Builder {
   void place(const float** slot, const std::vector<float>& v) { fix.push_back({slot, pk.add(v)}); }
 
   // Conv1d weight (Cout, Cin, k) -> [k][Cin][Cout]
-  // tc: 0 = fp32 SIMT only, 1 = also pack for the tensor-core conv, 2 = gated (cout = 2 * channels)
+  // tc: 0 = fp32 SIMT only, 1 = also pack for the tensor-core conv, 2 = gated (cout = 2 * channels),
+  //     3 = token-level GEMM: fp16 hi/lo split packing (rowgemm_tc_kernel)
   void conv(Lin& l, const std::string& base, int cout, int cin, int k, bool need_bias = true, int tc = 0) {
     const OnnxTensor& w = hv.need(base + ".weight", {cout, cin, k});
     std::vector<float> t(size_t(k) * cin * cout);
     for (int o = 0; o < cout; ++o)
       for (int i = 0; i < cin; ++i)
         for (int j = 0; j < k; ++j) t[(size_t(j) * cin + i) * cout + o] = w.f32[(size_t(o) * cin + i) * k + j];
-    if (tc && cin % 16 == 0 && (tc == 2 ? (cout / 2) % 16 == 0 : cout % 4 == 0))
+    if (tc == 3) rows_pack(l.rtc, t, k, cin, cout);
+    else if (tc && cin % 16 == 0 && (tc == 2 ? (cout / 2) % 16 == 0 : cout % 4 == 0))
       tc_pack(l.tc, t, k, cin, tc == 2 ? cout / 2 : cout, 1, tc == 2);
     place(&l.w, t);
     n_params += int64_t(t.size());
@@ -206,7 +237,7 @@ struct Builder {
       place(&d.sep_w[i], t);
       n_params += 3 * ch;
       vec(&d.sep_b[i], p + ".convs_sep." + is + ".bias", ch);
-      conv(d.c1x1[i], p + ".convs_1x1." + is, ch, ch, 1);
+      conv(d.c1x1[i], p + ".convs_1x1." + is, ch, ch, 1, true, 3);
       vec(&d.n1g[i], p + ".norms_1." + is + ".gamma", ch);
       vec(&d.n1b[i], p + ".norms_1." + is + ".beta", ch);
       vec(&d.n2g[i], p + ".norms_2." + is + ".gamma", ch);
@@ -232,6 +263,8 @@ std::unique_ptr<DeviceVoice> build_device_voice(const HostVoice& hv, int device)
     B.tc_fmt = dv.tc_fmt;
     const char* fs = getenv("M3B200_FORCE_SIMT");
     dv.use_tc = !(fs && *fs && *fs != '0');
+    const char* ft = getenv("M3B200_TEXT_SIMT");
+    dv.use_rows_tc = dv.use_tc && !(ft && *ft && *ft != '0');
   }
   const int H = c.hidden, I = c.inter, Ff = c.filter;
   const int dk = H / c.n_heads;
@@ -262,6 +295,7 @@ std::unique_ptr<DeviceVoice> build_device_voice(const HostVoice& hv, int device)
           b[s * H + o] = tb.f32[o];
         }
       }
+      B.rows_pack(L.qkv.rtc, w, 1, H, 3 * H);
       B.place(&L.qkv.w, w);
       B.place(&L.qkv.b, b);
       L.qkv.cin = H;
@@ -269,7 +303,7 @@ std::unique_ptr<DeviceVoice> build_device_voice(const HostVoice& hv, int device)
       L.qkv.taps = 1;
       B.n_params += int64_t(w.size() + b.size());
     }
-    B.conv(L.o, a + ".conv_o", H, H, 1);
+    B.conv(L.o, a + ".conv_o", H, H, 1, true, 3);
     {
       const OnnxTensor& ek = hv.need(a + ".emb_rel_k", {});
       const OnnxTensor& ev = hv.need(a + ".emb_rel_v", {});
@@ -285,10 +319,10 @@ std::unique_ptr<DeviceVoice> build_device_voice(const HostVoice& hv, int device)
     B.vec(&L.g2, "enc_p.encoder.norm_layers_2." + std::to_string(l) + ".gamma", H);
     B.vec(&L.b2, "enc_p.encoder.norm_layers_2." + std::to_string(l) + ".beta", H);
     const std::string f = "enc_p.encoder.ffn_layers." + std::to_string(l);
-    B.conv(L.ffn1, f + ".conv_1", Ff, H, c.kernel_size);
-    B.conv(L.ffn2, f + ".conv_2", H, Ff, c.kernel_size);
+    B.conv(L.ffn1, f + ".conv_1", Ff, H, c.kernel_size, true, 3);
+    B.conv(L.ffn2, f + ".conv_2", H, Ff, c.kernel_size, true, 3);
   }
-  B.conv(dv.enc_proj, "enc_p.proj", 2 * I, H, 1);
+  B.conv(dv.enc_proj, "enc_p.proj", 2 * I, H, 1, true, 3);
 
   // ---- speaker embedding & conditioning layers (collected into one G -> n_cond GEMM)
   const OnnxTensor* embg = hv.maybe("emb_g.weight");
@@ -320,8 +354,8 @@ std::unique_ptr<DeviceVoice> build_device_voice(const HostVoice& hv, int device)
   if (dv.use_sdp) {
     const int Fd = H;
     dv.dp_ch = Fd;
-    B.conv(dv.dp_pre, "dp.pre", Fd, H, 1);
-    B.conv(dv.dp_proj, "dp.proj", Fd, Fd, 1);
+    B.conv(dv.dp_pre, "dp.pre", Fd, H, 1, true, 3);
+    B.conv(dv.dp_proj, "dp.proj", Fd, Fd, 1, true, 3);
     B.dds(dv.dp_dds, "dp.convs", Fd);
     dv.dp_cond_off = add_cond("dp.cond", Fd);
     const OnnxTensor& m = hv.need("dp.flows.0.m", {2, 1});
@@ -343,7 +377,7 @@ std::unique_ptr<DeviceVoice> build_device_voice(const HostVoice& hv, int device)
       B.vec(&cf.pre_b, p + ".pre.bias", Fd);
       B.n_params += Fd;
       B.dds(cf.dds, p + ".convs", Fd);
-      B.conv(cf.proj, p + ".proj", 29, Fd, 1);
+      B.conv(cf.proj, p + ".proj", 29, Fd, 1, true, 3);
     }
   } else {
     const OnnxTensor& w1 = hv.need("dp.conv_1.weight", {});
@@ -743,8 +777,31 @@ struct Run {
   // token-level fp32 convs over packed rows
   const int4* rowinfo = nullptr;
   int n_rows = 0;
+  const int* vmap = nullptr;
+  int vrows = 0;
   void row_conv(const Lin& l, const float* in, int in_stride, float* out, int out_stride, int act = 0,
                 const float* ub = nullptr, int ub_stride = 0) const {
+    if (dv.use_rows_tc && l.rtc.ok && (l.taps == 1 || l.taps == 3)) {
+      RowGemmTcParams q;
+      q.in = in;
+      q.in_stride = in_stride;
+      q.K = l.cin;
+      q.w = dv.slab16 + l.rtc.woff;
+      q.N = l.cout;
+      q.taps = l.taps;
+      q.pad_left = (l.taps - 1) / 2;
+      q.bias = l.b;
+      q.ubias = ub;
+      q.ub_stride = ub_stride;
+      q.act = act;
+      q.out = out;
+      q.out_stride = out_stride;
+      q.vmap = vmap;
+      q.rowinfo = rowinfo;
+      q.vrows = vrows;
+      launch_rowgemm_tc(q, st);
+      return;
+    }
     RowConvParams p;
     p.in = in;
     p.in_stride = in_stride;
@@ -876,7 +933,7 @@ Result* run_inference(Voice& v, const int64_t* ids, const int64_t* lengths, int 
   // ---------------- phase 1 workspace (token level) ----------------
   {
     size_t fl = size_t(NT) * (size_t(H) * 3 + 3 * H + Ff + 2 * I + size_t(Fd) * 4 + 40) + size_t(batch) * (G + dv.n_cond + 8);
-    size_t bytes = fl * 4 + size_t(batch) * t_stride * 8 + size_t(batch) * 64 + (1 << 16) + 512 * 64 + size_t(NT) * 16;
+    size_t bytes = fl * 4 + size_t(batch) * t_stride * 8 + size_t(batch) * 64 + (1 << 16) + 512 * 64 + size_t(NT) * 16 + (size_t(NT) + batch) * 4;
     cx.a1.reserve(bytes);
   }
   Arena& A = cx.a1;
@@ -917,6 +974,10 @@ Result* run_inference(Voice& v, const int64_t* ids, const int64_t* lengths, int 
     launch_fill_rowinfo(d_rowinfo, d_tok_off, d_tok_len, batch, Tmax, st);
     R.rowinfo = d_rowinfo;
     R.n_rows = NT;
+    int* d_vmap = A.alloc<int>(size_t(NT) + batch);
+    launch_fill_vmap(d_vmap, d_tok_off, d_tok_len, batch, Tmax, st);
+    R.vmap = d_vmap;
+    R.vrows = NT + batch;
   }
 
   // ---------------- speaker conditioning ----------------

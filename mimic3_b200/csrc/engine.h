@@ -32,11 +32,17 @@ struct TcConvW {  // 16-bit tensor-core packing [chunk][tap][K/8][NC][8] (kernel
   int K = 0, NC = 0, n_chunks = 0, N = 0, taps = 1;
 };
 
+struct RowTcW {  // fp16 hi/lo split packing for rowgemm_tc_kernel (kernels_tc_rows.cu)
+  bool ok = false;
+  unsigned long long woff = 0;
+};
+
 struct Lin {  // a Conv1d packed as [taps][Cin][ldw] (+ bias[ldw])
   const float* w = nullptr;
   const float* b = nullptr;
   int cin = 0, cout = 0, taps = 1;
   TcConvW tc;
+  RowTcW rtc;
 };
 
 struct DDSW {
@@ -104,6 +110,7 @@ struct DeviceVoice {
   uint16_t* slab16 = nullptr;  // 16-bit tensor-core operands
   int tc_fmt = 1;              // 0 fp16, 1 bf16
   bool use_tc = true;
+  bool use_rows_tc = true;  // text-side GEMMs on tensor cores (fp16 x 3 split); M3B200_TEXT_SIMT=1 disables
   std::vector<MrfStageW> mrf;
   size_t slab_floats = 0;
   int64_t n_params = 0;

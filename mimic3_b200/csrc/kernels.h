@@ -112,6 +112,28 @@ struct TcConvParams {
 bool conv_tc_supported(int K, int NC, int taps, int dil);
 void launch_conv_tc(const TcConvParams& p, int fmt, int n_seg, int max_seg_len, cudaStream_t st);
 
+// Token-level conv-as-GEMM on tensor cores with fp16 hi/lo split operands (kernels_tc_rows.cu).
+// Weights: [chunk(64 cols)][K block(32)][tap][hi|lo][4][64][8], 16-bit.
+struct RowGemmTcParams {
+  const float* in = nullptr;
+  int in_stride = 0, K = 0;
+  const uint16_t* w = nullptr;
+  int N = 0, taps = 1, pad_left = 0;
+  const float* bias = nullptr;
+  const float* ubias = nullptr;
+  int ub_stride = 0;
+  int act = 0;
+  float* out = nullptr;
+  int out_stride = 0;
+  const int* vmap = nullptr;      // virtual row -> physical row, -1 for the zero row after each utterance
+  const int4* rowinfo = nullptr;  // physical row -> (lo, hi, seg, 0)
+  int vrows = 0;
+};
+bool rowgemm_tc_supported(int K, int taps);
+size_t rowgemm_tc_weight_elems(int K, int N, int taps);
+void launch_rowgemm_tc(const RowGemmTcParams& p, cudaStream_t st);
+void launch_fill_vmap(int* vmap, const int* seg_off, const int* seg_len, int n_seg, int max_len, cudaStream_t st);
+
 // Fused last generator stage: ConvTranspose + MRF + conv_post/tanh/peak (kernels_tc_dec.cu).
 struct DecConv {
   unsigned long long woff = 0;  // element offset of [tap][K/8][N][8] in w16

@@ -1,0 +1,211 @@
+// Token-level Conv1d-as-GEMM on tensor cores with fp32-equivalent products ("fp16 x 3"):
+//     a = a_hi + a_lo / 2048,   a_hi = fp16(a),  a_lo = fp16((a - a_hi) * 2048)      (same for w)
+//     a*w ~= a_hi*w_hi + (a_hi*w_lo + a_lo*w_hi) / 2048          (dropped term: 2^-22 relative)
+// Two fp32 TMEM accumulators per tile (main, correction), three tcgen05.mma per K-step.  This is what
+// lets the text encoder / duration predictor leave the fp32 FFMA pipe without moving `logw` (a 1-ulp
+// class change there can add a whole frame, SURVEY.md hard part 2).
+//
+// Rows are the packed tokens of all utterances with ONE virtual zero row after each utterance, so a
+// k=3 tap is a descriptor shift even across utterance boundaries (vmap[v] = physical row or -1).
+// CTA = 128 virtual rows x 64 output columns; K streamed in blocks of 32 through a 2-stage ring:
+//   warps 0-3  convert the fp32 A block to hi/lo fp16 (interleaved layout) -- and run the epilogue;
+//   warp 4     one thread: bulk-copies the pre-split weight block of all taps (one copy per stage);
+//   warp 5     one thread: issues the MMAs, frees stages with tcgen05.commit.
+#include <stdexcept>
+
+#include "kernels.h"
+#include "tc_common.cuh"
+
+namespace m3 {
+
+constexpr int RG_KB = 32;       // K block
+constexpr int RG_NC = 64;       // output columns per CTA
+constexpr int RG_STAGES = 2;
+constexpr int RG_THREADS = 192;
+
+__global__ void fill_vmap_kernel(int* vmap, const int* seg_off, const int* seg_len, int n_seg) {
+  const int seg = blockIdx.y;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int len = seg_len[seg];
+  if (t > len) return;
+  const int v = seg_off[seg] + seg + t;  // one gap row after every utterance
+  vmap[v] = t < len ? seg_off[seg] + t : -1;
+}
+
+void launch_fill_vmap(int* vmap, const int* seg_off, const int* seg_len, int n_seg, int max_len, cudaStream_t st) {
+  if (max_len <= 0) return;
+  fill_vmap_kernel<<<dim3((max_len + 1 + 127) / 128, n_seg), 128, 0, st>>>(vmap, seg_off, seg_len, n_seg);
+  post_launch("fill_vmap_kernel", st);
+}
+
+__global__ void __launch_bounds__(RG_THREADS, 2) rowgemm_tc_kernel(RowGemmTcParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint32_t tmem_slot;
+  __shared__ __align__(8) uint64_t a_full[RG_STAGES], w_full[RG_STAGES], empty_bar[RG_STAGES], acc_full;
+
+  const int v0 = blockIdx.x * 128;
+  const int chunk = blockIdx.y;
+  const int taps = p.taps;
+  const int RA = (128 + taps - 1) | 1;                 // A rows per stage (odd pitch)
+  const uint32_t a_bytes = 2u * (RG_KB / 8) * RA * 16; // hi + lo
+  const uint32_t w_bytes = uint32_t(taps) * 2u * RG_KB * RG_NC * 2;
+  const uint32_t a_pad = (a_bytes + 127u) & ~127u;
+  const uint32_t stage_bytes = a_pad + w_bytes;
+  const int nkb = p.K / RG_KB;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (warp == 0) tc::tmem_alloc<128>(&tmem_slot);
+  if (tid == 32) {
+    for (int s = 0; s < RG_STAGES; ++s) {
+      tc::mbar_init(&a_full[s], 4);
+      tc::mbar_init(&w_full[s], 1);
+      tc::mbar_init(&empty_bar[s], 1);
+    }
+    tc::mbar_init(&acc_full, 1);
+    tc::mbar_fence_init();
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+
+  if (warp < 4) {
+    // ===================== A stagers (then epilogue) =====================
+    const int pad_left = p.pad_left;
+    const int items = (RG_KB / 8) * RA;  // (row, 8-channel chunk) per stage, 128 threads
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % RG_STAGES;
+      tc::mbar_wait(&empty_bar[s], (((kb / RG_STAGES) & 1) ^ 1));
+      uint8_t* abuf = smem + size_t(s) * stage_bytes;
+      for (int idx = tid; idx < items; idx += 128) {
+        const int rr = idx / (RG_KB / 8), c8 = idx - rr * (RG_KB / 8);
+        const int v = v0 - pad_left + rr;
+        uint4 hi = make_uint4(0u, 0u, 0u, 0u), lo = hi;
+        if (v >= 0 && v < p.vrows) {
+          const int phys = p.vmap[v];
+          if (phys >= 0) {
+            const float* src = p.in + (long long)phys * p.in_stride + kb * RG_KB + c8 * 8;
+            const float4 a = *reinterpret_cast<const float4*>(src);
+            const float4 b = *reinterpret_cast<const float4*>(src + 4);
+            const float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+            uint32_t h[4], l[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const __half2 hh = __floats2half2_rn(f[2 * e], f[2 * e + 1]);
+              const float2 back = __half22float2(hh);
+              const __half2 ll = __floats2half2_rn((f[2 * e] - back.x) * 2048.f, (f[2 * e + 1] - back.y) * 2048.f);
+              h[e] = *reinterpret_cast<const uint32_t*>(&hh);
+              l[e] = *reinterpret_cast<const uint32_t*>(&ll);
+            }
+            hi = make_uint4(h[0], h[1], h[2], h[3]);
+            lo = make_uint4(l[0], l[1], l[2], l[3]);
+          }
+        }
+        *reinterpret_cast<uint4*>(abuf + (size_t(c8) * RA + rr) * 16) = hi;
+        *reinterpret_cast<uint4*>(abuf + (size_t(RG_KB / 8 + c8) * RA + rr) * 16) = lo;
+      }
+      tc::fence_async_smem();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&a_full[s]);
+    }
+    // ---- epilogue: out = main + corr/2048 + bias ----
+    tc::mbar_wait(&acc_full, 0);
+    tc::fence_after_sync();
+    const int v = v0 + warp * 32 + lane;
+    const int phys = (v < p.vrows) ? p.vmap[v] : -1;
+    const uint32_t lane_base = tmem + (uint32_t(warp * 32) << 16);
+    const int seg = (p.ubias && phys >= 0) ? p.rowinfo[phys].z : 0;
+    for (int c0 = 0; c0 < RG_NC; c0 += 16) {
+      __syncwarp();
+      float m[16], c[16];
+      tc::tmem_ld16(lane_base + c0, m);
+      tc::tmem_ld16(lane_base + RG_NC + c0, c);
+      tc::tmem_ld_wait();
+      if (phys < 0) continue;
+      const int n0 = chunk * RG_NC + c0;
+      float* dst = p.out + (long long)phys * p.out_stride + n0;
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        const int n = n0 + e;
+        if (n >= p.N) break;
+        float val = m[e] + c[e] * (1.0f / 2048.0f);
+        if (p.bias) val += p.bias[n];
+        if (p.ubias) val += p.ubias[(long long)seg * p.ub_stride + n];
+        if (p.act == 1) val = fmaxf(val, 0.f);
+        dst[e] = val;
+      }
+    }
+  } else if (warp == 4) {
+    // ===================== weight producer =====================
+    if (tc::elect_one()) {
+      const uint16_t* src = p.w + size_t(chunk) * nkb * (size_t(taps) * 2 * RG_KB * RG_NC);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % RG_STAGES;
+        tc::mbar_wait(&empty_bar[s], (((kb / RG_STAGES) & 1) ^ 1));
+        tc::mbar_expect_tx(&w_full[s], w_bytes);
+        tc::bulk_g2s(smem + size_t(s) * stage_bytes + a_pad, src + size_t(kb) * (size_t(taps) * 2 * RG_KB * RG_NC), w_bytes,
+                     &w_full[s]);
+      }
+    }
+  } else {
+    // ===================== MMA issuer =====================
+    if (tc::elect_one()) {
+      const uint32_t idesc = tc::make_idesc(128, RG_NC, 0);
+      const uint32_t d_main = tmem, d_corr = tmem + RG_NC;
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % RG_STAGES;
+        const uint32_t ph = (kb / RG_STAGES) & 1;
+        tc::mbar_wait(&a_full[s], ph);
+        tc::mbar_wait(&w_full[s], ph);
+        tc::fence_after_sync();
+        const uint32_t abase = tc::smem_u32(smem + size_t(s) * stage_bytes);
+        const uint32_t wbase = abase + a_pad;
+        for (int tap = 0; tap < taps; ++tap) {
+#pragma unroll
+          for (int ks = 0; ks < RG_KB / 16; ++ks) {
+            const uint32_t a_hi = abase + uint32_t((ks * 2) * RA + tap) * 16u;
+            const uint32_t a_lo = abase + uint32_t((RG_KB / 8 + ks * 2) * RA + tap) * 16u;
+            const uint32_t w_hi = wbase + uint32_t(((tap * 2 + 0) * (RG_KB / 8) + ks * 2) * RG_NC) * 16u;
+            const uint32_t w_lo = wbase + uint32_t(((tap * 2 + 1) * (RG_KB / 8) + ks * 2) * RG_NC) * 16u;
+            const uint64_t dah = tc::make_desc(a_hi, uint32_t(RA) * 16u, 128u), dal = tc::make_desc(a_lo, uint32_t(RA) * 16u, 128u);
+            const uint64_t dwh = tc::make_desc(w_hi, RG_NC * 16u, 128u), dwl = tc::make_desc(w_lo, RG_NC * 16u, 128u);
+            const uint32_t first = (kb | tap | ks) ? 1u : 0u;
+            tc::mma_f16_ss(d_main, dah, dwh, idesc, first);
+            tc::mma_f16_ss(d_corr, dah, dwl, idesc, first);
+            tc::mma_f16_ss(d_corr, dal, dwh, idesc, 1u);
+          }
+        }
+        tc::mma_commit(&empty_bar[s]);
+      }
+      tc::mma_commit(&acc_full);
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc<128>(tmem);
+}
+
+bool rowgemm_tc_supported(int K, int taps) { return K % RG_KB == 0 && K >= RG_KB && (taps == 1 || taps == 3); }
+
+size_t rowgemm_tc_weight_elems(int K, int N, int taps) {
+  const int chunks = (N + RG_NC - 1) / RG_NC;
+  return size_t(chunks) * (K / RG_KB) * taps * 2 * RG_KB * RG_NC;
+}
+
+void launch_rowgemm_tc(const RowGemmTcParams& p, cudaStream_t st) {
+  if (p.vrows <= 0) return;
+  const int RA = (128 + p.taps - 1) | 1;
+  const size_t a_pad = (size_t(2) * (RG_KB / 8) * RA * 16 + 127) & ~size_t(127);
+  const size_t smem = RG_STAGES * (a_pad + size_t(p.taps) * 2 * RG_KB * RG_NC * 2);
+  static thread_local size_t configured = 0;
+  if (configured < smem) {
+    if (cudaFuncSetAttribute(rowgemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
+      throw std::runtime_error("rowgemm_tc: cannot reserve shared memory");
+    configured = smem;
+  }
+  dim3 grid((p.vrows + 127) / 128, (p.N + RG_NC - 1) / RG_NC);
+  rowgemm_tc_kernel<<<grid, RG_THREADS, smem, st>>>(p);
+  post_launch("rowgemm_tc_kernel", st);
+}
+
+}  // namespace m3

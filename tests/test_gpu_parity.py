@@ -287,3 +287,29 @@ def test_mixed_voice_residency_cfg5(voices, built_library):
             np.testing.assert_array_equal(again, first[n])
     for s in sess.values():
         s.close()
+
+
+def test_text_side_tensor_core_split_keeps_durations(voices, built_library, monkeypatch):
+    """The fp16 hi/lo split GEMMs (3 MMAs per product) of the text encoder / duration predictor must
+    reproduce the fp32 FFMA path: identical integer durations on 256 x 80 ids, logw within fp32 noise."""
+    from mimic3_b200.engine import B200Session
+    rng = np.random.Generator(np.random.PCG64(1234))
+    ids = rng.integers(4, 50, size=(256, 80)).astype(np.int64)
+    lens = np.full(256, 80, dtype=np.int64)
+    sid = (np.arange(256) % 109).astype(np.int64)
+    monkeypatch.setenv("M3B200_TEXT_SIMT", "1")
+    ref_s = B200Session(str(voices("low_ms")))
+    monkeypatch.delenv("M3B200_TEXT_SIMT")
+    tc_s = B200Session(str(voices("low_ms")))
+    for scales, seed in (((0.0, 1.0, 0.0), 0), ((0.667, 1.0, 0.8), 99)):
+        a = ref_s.infer(ids, lens, scales, sid, seed=seed, debug_tensors=("durations", "logw", "x"))
+        b = tc_s.infer(ids, lens, scales, sid, seed=seed, debug_tensors=("durations", "logw", "x"))
+        dl = np.abs(a.tensors["logw"] - b.tensors["logw"]).max()
+        dx = np.abs(a.tensors["x"] - b.tensors["x"]).max()
+        flips = int((a.tensors["durations"] != b.tensors["durations"]).sum())
+        print(f"scales {scales}: max|dlogw| {dl:.2e}  max|dx| {dx:.2e}  duration flips {flips} / {a.tensors['durations'].size}")
+        assert flips == 0
+        assert dl < 5e-5 and dx < 5e-4
+        np.testing.assert_array_equal(a.frames, b.frames)
+    ref_s.close()
+    tc_s.close()
