@@ -11,6 +11,8 @@ namespace m3 {
 
 extern thread_local int64_t g_launch_count;  // kernels launched by this thread's current call
 void post_launch(const char* what, cudaStream_t st);
+// Raises a kernel's dynamic shared-memory limit to the opt-in maximum exactly once (process-wide, thread safe).
+void ensure_max_dynamic_smem(const void* func);
 
 struct ConvParams {
   // input

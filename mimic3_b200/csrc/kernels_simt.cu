@@ -6,6 +6,8 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <mutex>
+#include <set>
 #include <stdexcept>
 
 #include "kernels.h"
@@ -28,6 +30,19 @@ void post_launch(const char* what, cudaStream_t st) {
     snprintf(buf, sizeof buf, "kernel %s failed: %s", what, cudaGetErrorString(err));
     throw std::runtime_error(buf);
   }
+}
+void ensure_max_dynamic_smem(const void* func) {
+  static std::mutex mu;
+  static std::set<const void*> done;
+  std::lock_guard<std::mutex> lk(mu);
+  if (done.count(func)) return;
+  // 227 KB opt-in maximum minus room for static shared memory; the limit is only ever raised, never
+  // lowered, so concurrent launches with different sizes cannot invalidate each other.
+  if (cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024) != cudaSuccess) {
+    cudaGetLastError();
+    throw std::runtime_error("cannot raise the dynamic shared-memory limit of a kernel");
+  }
+  done.insert(func);
 }
 #define M3_LAUNCHED() post_launch(__func__, st)
 
@@ -706,7 +721,7 @@ void launch_attention(const float* qkv, const float* emb_rel_k, const float* emb
   const int ne = (dk + 15) / 16;
 #define M3_ATTN(NE)                                                                                          \
   {                                                                                                          \
-    cudaFuncSetAttribute(attention_kernel<NE>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));      \
+    ensure_max_dynamic_smem(reinterpret_cast<const void*>(attention_kernel<NE>));                           \
     attention_kernel<NE><<<grid, 256, smem, st>>>(qkv, emb_rel_k, emb_rel_v, out, H, dk, window, seg_off,    \
                                                    seg_len);                                                 \
   }
@@ -1012,11 +1027,7 @@ void launch_conv_post(const float* x, int C, const float* w, int k, float slope,
   if (max_len <= 0) return;
   if (C % 4) throw std::runtime_error("conv_post: channel count must be a multiple of 4");
   const size_t smem = sizeof(float) * (size_t(k) * C + size_t(256 + k - 1) * (C + 1));
-  static thread_local size_t configured = 0;
-  if (smem > 48 * 1024 && configured < smem) {
-    cudaFuncSetAttribute(conv_post_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-    configured = smem;
-  }
+  if (smem > 48 * 1024) ensure_max_dynamic_smem(reinterpret_cast<const void*>(conv_post_kernel));
   conv_post_kernel<<<dim3((max_len * scale + 255) / 256, n_seg), 256, smem, st>>>(x, C, w, k, slope, audio,
                                                                                   peak_bits, seg_off, seg_len, scale);
   M3_LAUNCHED();

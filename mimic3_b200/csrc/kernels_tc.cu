@@ -325,12 +325,7 @@ static void launch_mrf_inst(const MrfParams& p, int n_seg, int max_len, cudaStre
   if (q.stride <= 0) throw std::runtime_error("mrf_tc: receptive field exceeds the window");
   const size_t smem = size_t(C / 8) * 16 * (size_t((R + 2 * p.HX) | 1) + size_t((R + 2 * p.HY) | 1)) + size_t(2) * p.wg * C * C * 2;
   auto kern = mrf_tc_kernel<C, NT, FMT, NW, MINB>;
-  static thread_local size_t configured = 0;
-  if (configured < smem) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
-      throw std::runtime_error("mrf_tc: cannot reserve shared memory");
-    configured = smem;
-  }
+  ensure_max_dynamic_smem(reinterpret_cast<const void*>(kern));
   const int L = max_len * p.scale;
   dim3 grid((L + q.stride - 1) / q.stride, n_seg);
   kern<<<grid, NW * 32, smem, st>>>(q);

@@ -295,13 +295,7 @@ void launch_conv_tc(const TcConvParams& p, int fmt, int n_seg, int max_seg_len, 
   // >= 120 KB keeps a single CTA per SM (each CTA owns all 512 TMEM columns)
   const size_t smem = std::max(a_bytes + stages * stage, size_t(120 * 1024));
   dim3 grid((rows + CT_R - 1) / CT_R, n_seg);
-  static thread_local bool configured[2] = {false, false};
-  if (!configured[fmt ? 1 : 0]) {
-    cudaError_t e = fmt ? cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM_MAX)
-                        : cudaFuncSetAttribute(conv_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM_MAX);
-    if (e != cudaSuccess) throw std::runtime_error("conv_tc: cannot reserve shared memory");
-    configured[fmt ? 1 : 0] = true;
-  }
+  ensure_max_dynamic_smem(fmt ? reinterpret_cast<const void*>(conv_tc_kernel<1>) : reinterpret_cast<const void*>(conv_tc_kernel<0>));
   if (fmt) conv_tc_kernel<1><<<grid, CT_THREADS, smem, st>>>(p, stages, rows_a);
   else conv_tc_kernel<0><<<grid, CT_THREADS, smem, st>>>(p, stages, rows_a);
   post_launch("conv_tc_kernel", st);

@@ -322,12 +322,7 @@ static void launch_dec_inst(const DecStageParams& p, int n_seg, int max_len, cud
   if (q.stride <= 0) throw std::runtime_error("dec_last: receptive field exceeds the window");
   const size_t smem = dec_last_smem_bytes(C, NT, p.cin, p.up.taps, p.HX, p.HY, p.wb_bytes);
   auto kern = dec_last_kernel<C, NT, FMT>;
-  static thread_local size_t configured = 0;
-  if (configured < smem) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
-      throw std::runtime_error("dec_last: cannot reserve shared memory");
-    configured = smem;
-  }
+  ensure_max_dynamic_smem(reinterpret_cast<const void*>(kern));
   const int L = max_len * p.scale;
   dim3 grid((L + q.stride - 1) / q.stride, n_seg);
   kern<<<grid, 256, smem, st>>>(q);

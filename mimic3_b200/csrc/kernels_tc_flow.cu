@@ -356,13 +356,7 @@ bool flow_tc_supported(int Hc, int half, int nl, int kernel) {
 void launch_flow_tc(const FlowTcParams& p, int fmt, int n_seg, int max_len, cudaStream_t st) {
   if (n_seg <= 0 || max_len <= 0) return;
   const size_t smem = flow_tc_smem_bytes(p.Hc, p.half, p.nl);
-  static thread_local bool configured[2] = {false, false};
-  if (!configured[fmt ? 1 : 0]) {
-    cudaError_t e = fmt ? cudaFuncSetAttribute(flow_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024)
-                        : cudaFuncSetAttribute(flow_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
-    if (e != cudaSuccess) throw std::runtime_error("flow_tc: cannot reserve shared memory");
-    configured[fmt ? 1 : 0] = true;
-  }
+  ensure_max_dynamic_smem(fmt ? reinterpret_cast<const void*>(flow_tc_kernel<1>) : reinterpret_cast<const void*>(flow_tc_kernel<0>));
   const int stride = 128 - 4 * p.nl;
   dim3 grid((max_len + stride - 1) / stride, n_seg);
   if (fmt) flow_tc_kernel<1><<<grid, FL_THREADS, smem, st>>>(p);

@@ -197,12 +197,7 @@ void launch_rowgemm_tc(const RowGemmTcParams& p, cudaStream_t st) {
   const int RA = (128 + p.taps - 1) | 1;
   const size_t a_pad = (size_t(2) * (RG_KB / 8) * RA * 16 + 127) & ~size_t(127);
   const size_t smem = RG_STAGES * (a_pad + size_t(p.taps) * 2 * RG_KB * RG_NC * 2);
-  static thread_local size_t configured = 0;
-  if (configured < smem) {
-    if (cudaFuncSetAttribute(rowgemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
-      throw std::runtime_error("rowgemm_tc: cannot reserve shared memory");
-    configured = smem;
-  }
+  ensure_max_dynamic_smem(reinterpret_cast<const void*>(rowgemm_tc_kernel));
   dim3 grid((p.vrows + 127) / 128, (p.N + RG_NC - 1) / RG_NC);
   rowgemm_tc_kernel<<<grid, RG_THREADS, smem, st>>>(p);
   post_launch("rowgemm_tc_kernel", st);
