@@ -38,7 +38,13 @@ void ensure_max_dynamic_smem(const void* func) {
   if (done.count(func)) return;
   // 227 KB opt-in maximum minus room for static shared memory; the limit is only ever raised, never
   // lowered, so concurrent launches with different sizes cannot invalidate each other.
-  if (cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024) != cudaSuccess) {
+  cudaFuncAttributes fa;
+  int optin = 227 * 1024, dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  if (cudaFuncGetAttributes(&fa, func) != cudaSuccess) fa.sharedSizeBytes = 4096;
+  const int dyn_max = optin - int(fa.sharedSizeBytes);  // static + dynamic must fit the opt-in maximum
+  if (cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max) != cudaSuccess) {
     cudaGetLastError();
     throw std::runtime_error("cannot raise the dynamic shared-memory limit of a kernel");
   }
