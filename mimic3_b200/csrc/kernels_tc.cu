@@ -355,6 +355,7 @@ void launch_mrf_tc(const MrfParams& p, int C, int fmt, int n_seg, int max_len, c
     else launch_mrf_inst<CC, NT, 0, NW, MINB>(q, n_seg, max_len, st);                     \
   }
   static const int nt32 = [] { const char* e = getenv("M3B200_MRF_NT32"); return e ? atoi(e) : 4; }();
+  static const int mrf_warps = [] { const char* e = getenv("M3B200_MRF_WARPS"); return e ? atoi(e) : 16; }();
   static const int nt64 = [] { const char* e = getenv("M3B200_MRF_NT64"); return e ? atoi(e) : 2; }();
   if (C == 32) {
     q.wg = pick_wg(16 * 1024);  // whole conv (<= 14 KB) per buffer; ~100 KB/CTA -> 2 CTAs/SM
@@ -364,10 +365,12 @@ void launch_mrf_tc(const MrfParams& p, int C, int fmt, int n_seg, int max_len, c
   } else if (C == 64) {
     q.wg = pick_wg(16 * 1024);  // 2 taps per buffer; ~109 KB/CTA -> 2 CTAs/SM
     if (nt64 == 4) M3_MRF(64, 4, 8, 1)
+    else if (mrf_warps == 16) M3_MRF(64, 2, 16, 2)
     else M3_MRF(64, 2, 8, 2)
   } else if (C == 128) {
     q.wg = pick_wg(32 * 1024);  // 1 tap per buffer
-    M3_MRF(128, 2, 8, 1)
+    if (mrf_warps == 16) M3_MRF(128, 2, 16, 1)
+    else M3_MRF(128, 2, 8, 1)
   } else {
     throw std::runtime_error("mrf_tc: unsupported channel count");
   }

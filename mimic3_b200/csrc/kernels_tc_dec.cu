@@ -31,12 +31,15 @@ __device__ __forceinline__ void cpa_commit() { asm volatile("cp.async.commit_gro
 __device__ __forceinline__ void cpa_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 }  // namespace
 
-template <int C, int NT, int FMT>
-__global__ void __launch_bounds__(256, 2) dec_last_kernel(DecStageParams p) {
+template <int C, int NT, int FMT, int NW>
+__global__ void __launch_bounds__(NW * 32, 2) dec_last_kernel(DecStageParams p) {
+  constexpr int NTHR = NW * 32;
   constexpr int R = NT * 128;
   constexpr int CH = C / 8;
-  constexpr int HC = C / 2;      // columns per epilogue thread (8 warps = 4 lane quarters x 2 column halves)
-  constexpr int NCC = HC / 16;
+  constexpr int HC = C / (NW / 4);   // columns per epilogue thread (NW warps = 4 lane quarters x NW/4 column groups)
+  constexpr int G = HC >= 16 ? 16 : 8;  // columns per tcgen05.ld / st
+  constexpr int NCC = HC / G;
+  static_assert(HC % 8 == 0 && HC >= 8, "column split");
   constexpr int TCOLS_RAW = 2 * NT * C;
   constexpr int TCOLS = TCOLS_RAW <= 64 ? 64 : TCOLS_RAW <= 128 ? 128 : TCOLS_RAW <= 256 ? 256 : 512;
   static_assert(TCOLS_RAW <= 512, "TMEM budget");
@@ -75,12 +78,12 @@ __global__ void __launch_bounds__(256, 2) dec_last_kernel(DecStageParams p) {
     const uint4* __restrict__ src = reinterpret_cast<const uint4*>(p.w16 + cv.woff + size_t(g0) * cv.K * cv.N);
     uint4* dst = reinterpret_cast<uint4*>(wbuf + size_t(buf) * wb_bytes);
     const int n16 = ntap * cv.K * cv.N / 8;
-    for (int i = tid; i < n16; i += 256) cpa16(dst + i, src + i);
+    for (int i = tid; i < n16; i += NTHR) cpa16(dst + i, src + i);
     cpa_commit();
   };
   prefetch(0, 0, 0);
 
-  for (int i = tid; i < 6 * C; i += 256) {
+  for (int i = tid; i < 6 * C; i += NTHR) {
     const int j = i / C, c = i - j * C;
     float v = 0.f;
     if (j == 0) v = p.up_bias[c];
@@ -100,7 +103,7 @@ __global__ void __launch_bounds__(256, 2) dec_last_kernel(DecStageParams p) {
     const int s0 = w0 - p.up.pad_left;
     const int items = CHI * ROWSU;
     auto lr = [](float v) { return v >= 0.f ? v : 0.1f * v; };
-    for (int idx = tid; idx < items; idx += 256) {
+    for (int idx = tid; idx < items; idx += NTHR) {
       const int sr = idx / CHI, c8 = idx - sr * CHI;
       const int s = s0 + sr;
       uint4 pk = make_uint4(0u, 0u, 0u, 0u);
@@ -119,7 +122,7 @@ __global__ void __launch_bounds__(256, 2) dec_last_kernel(DecStageParams p) {
       *reinterpret_cast<uint4*>(bufU + (size_t(c8) * ROWSU + sr) * 16) = pk;
     }
     // bufX rows outside the window's own [0, R) are never produced: keep them zero
-    for (int idx = tid; idx < CH * ROWSX; idx += 256) {
+    for (int idx = tid; idx < CH * ROWSX; idx += NTHR) {
       const int rr = idx % ROWSX;
       if (rr < p.HX || rr >= R + p.HX) *reinterpret_cast<uint4*>(bufX + size_t(idx) * 16) = make_uint4(0u, 0u, 0u, 0u);
     }
@@ -133,7 +136,7 @@ __global__ void __launch_bounds__(256, 2) dec_last_kernel(DecStageParams p) {
   uint32_t gphase[2] = {0u, 0u}, tphase = 0;
   int gi = 0;
   bool prev_nonlast = false;
-  float xr[NT][NCC][16];  // x of this thread's rows / columns, fp32 (residual stream source)
+  float xr[NT][NCC][G];  // x of this thread's rows / columns, fp32 (residual stream source)
 
   for (int s = 0; s < p.nsteps; ++s) {
     const DecConv cv = p.steps[s];
@@ -192,6 +195,13 @@ __global__ void __launch_bounds__(256, 2) dec_last_kernel(DecStageParams p) {
       }
     }
     // ------------------------------ epilogues ------------------------------
+    // thread <-> (row = lane quarter q*32+lane of tile m, column group hhalf: HC columns in groups of G)
+    auto store_ops = [&](uint8_t* buf, int pitch, int row, int col, const uint32_t* pk) {
+      uint8_t* dst = buf + (size_t(col / 8) * pitch + row) * 16;
+#pragma unroll
+      for (int i = 0; i < G / 8; ++i)
+        *reinterpret_cast<uint4*>(dst + size_t(i) * pitch * 16) = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+    };
 #pragma unroll
     for (int m = 0; m < NT; ++m) {
       tc::mbar_wait(&tbar[m], tphase);
@@ -203,88 +213,82 @@ __global__ void __launch_bounds__(256, 2) dec_last_kernel(DecStageParams p) {
         // x = T + b_up: keep in registers, publish lrelu(x) as the resblocks' A operand, seed T for resblock 0
 #pragma unroll
         for (int cc = 0; cc < NCC; ++cc) {
-          const int col = hhalf * HC + cc * 16;
-          float v[16];
-          tc::tmem_ld16(lane_base + T0 + m * C + col, v);
+          const int col = hhalf * HC + cc * G;
+          float v[G];
+          tc::tmem_ldg<G>(lane_base + T0 + m * C + col, v);
           tc::tmem_ld_wait();
-          uint32_t pk[8];
+          uint32_t pk[G / 2];
 #pragma unroll
-          for (int e = 0; e < 16; ++e) xr[m][cc][e] = v[e] + sbias[0][col + e];
+          for (int e = 0; e < G; ++e) xr[m][cc][e] = v[e] + sbias[0][col + e];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
+          for (int e = 0; e < G / 2; ++e) {
             float a = xr[m][cc][2 * e], b = xr[m][cc][2 * e + 1];
             a = a >= 0.f ? a : 0.1f * a;
             b = b >= 0.f ? b : 0.1f * b;
             pk[e] = inside ? E::pack2(a, b) : 0u;
           }
-          uint8_t* dst = bufX + (size_t(col / 8) * ROWSX + r + p.HX) * 16;
-          *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          *reinterpret_cast<uint4*>(dst + size_t(ROWSX) * 16) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          store_ops(bufX, ROWSX, r + p.HX, col, pk);
 #pragma unroll
-          for (int e = 0; e < 16; ++e) v[e] = xr[m][cc][e] + sbias[1][col + e];
-          tc::tmem_st16(lane_base + T0 + m * C + col, v);
+          for (int e = 0; e < G; ++e) v[e] = xr[m][cc][e] + sbias[1][col + e];
+          tc::tmem_stg<G>(lane_base + T0 + m * C + col, v);
         }
       } else if (kind == 1) {
 #pragma unroll
         for (int cc = 0; cc < NCC; ++cc) {
-          const int col = hhalf * HC + cc * 16;
-          float v[16];
-          tc::tmem_ld16(lane_base + T0 + m * C + col, v);
+          const int col = hhalf * HC + cc * G;
+          float v[G];
+          tc::tmem_ldg<G>(lane_base + T0 + m * C + col, v);
           tc::tmem_ld_wait();
-          uint32_t pk[8];
+          uint32_t pk[G / 2];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
+          for (int e = 0; e < G / 2; ++e) {
             float a = v[2 * e], b = v[2 * e + 1];
             a = a >= 0.f ? a : 0.1f * a;
             b = b >= 0.f ? b : 0.1f * b;
             pk[e] = inside ? E::pack2(a, b) : 0u;
           }
-          uint8_t* dst = bufY + (size_t(col / 8) * ROWSY + r + p.HY) * 16;
-          *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          *reinterpret_cast<uint4*>(dst + size_t(ROWSY) * 16) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          store_ops(bufY, ROWSY, r + p.HY, col, pk);
         }
       } else if (kind == 2) {
         const int j = cv.rb;
         const bool first = j == 0, last = j == p.nk - 1;
 #pragma unroll
         for (int cc = 0; cc < NCC; ++cc) {
-          const int col = hhalf * HC + cc * 16;
-          float v[16];
-          tc::tmem_ld16(lane_base + T0 + m * C + col, v);
+          const int col = hhalf * HC + cc * G;
+          float v[G];
+          tc::tmem_ldg<G>(lane_base + T0 + m * C + col, v);
           if (!first) {
-            float sv[16];
-            tc::tmem_ld16(lane_base + S0 + m * C + col, sv);
+            float sv[G];
+            tc::tmem_ldg<G>(lane_base + S0 + m * C + col, sv);
             tc::tmem_ld_wait();
 #pragma unroll
-            for (int e = 0; e < 16; ++e) v[e] += sv[e];
+            for (int e = 0; e < G; ++e) v[e] += sv[e];
           } else {
             tc::tmem_ld_wait();
           }
           if (!last) {
-            tc::tmem_st16(lane_base + S0 + m * C + col, v);
-            float t2[16];  // seed T for the next resblock: x + its first-conv bias
+            tc::tmem_stg<G>(lane_base + S0 + m * C + col, v);
+            float t2[G];  // seed T for the next resblock: x + its first-conv bias
 #pragma unroll
-            for (int e = 0; e < 16; ++e) t2[e] = xr[m][cc][e] + sbias[j + 2][col + e];
-            tc::tmem_st16(lane_base + T0 + m * C + col, t2);
+            for (int e = 0; e < G; ++e) t2[e] = xr[m][cc][e] + sbias[j + 2][col + e];
+            tc::tmem_stg<G>(lane_base + T0 + m * C + col, t2);
           } else {
             // out = (sum + late bias) / nk ; A operand of conv_post = lrelu(out, 0.01)
-            uint32_t pk[8];
+            uint32_t pk[G / 2];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
+            for (int e = 0; e < G / 2; ++e) {
               float a = (v[2 * e] + sbias[5][col + 2 * e]) * p.inv_nk;
               float b = (v[2 * e + 1] + sbias[5][col + 2 * e + 1]) * p.inv_nk;
               a = a >= 0.f ? a : 0.01f * a;
               b = b >= 0.f ? b : 0.01f * b;
               pk[e] = inside ? E::pack2(a, b) : 0u;
             }
-            uint8_t* dst = bufX + (size_t(col / 8) * ROWSX + r + p.HX) * 16;
-            *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            *reinterpret_cast<uint4*>(dst + size_t(ROWSX) * 16) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            store_ops(bufX, ROWSX, r + p.HX, col, pk);
           }
         }
       } else {  // kind == 3: y = tanh(column 0), per-utterance peak
-        float v[16];
-        tc::tmem_ld16(lane_base + T0 + m * C, v);
+        float v[8];
+        tc::tmem_ld8(lane_base + T0 + m * C, v);
         tc::tmem_ld_wait();
         float y = 0.f;
         const bool store = hhalf == 0 && r >= p.H && r < R - p.H && g < L;
@@ -314,18 +318,18 @@ size_t dec_last_smem_bytes(int C, int NT, int cin, int up_taps, int HX, int HY, 
   return x + ((std::max(u, y) + 15) & ~size_t(15)) + 2 * size_t(wb_bytes) + 64;
 }
 
-template <int C, int NT, int FMT>
+template <int C, int NT, int FMT, int NW>
 static void launch_dec_inst(const DecStageParams& p, int n_seg, int max_len, cudaStream_t st) {
   DecStageParams q = p;
   const int R = NT * 128;
   q.stride = R - 2 * p.H;
   if (q.stride <= 0) throw std::runtime_error("dec_last: receptive field exceeds the window");
   const size_t smem = dec_last_smem_bytes(C, NT, p.cin, p.up.taps, p.HX, p.HY, p.wb_bytes);
-  auto kern = dec_last_kernel<C, NT, FMT>;
+  auto kern = dec_last_kernel<C, NT, FMT, NW>;
   ensure_max_dynamic_smem(reinterpret_cast<const void*>(kern));
   const int L = max_len * p.scale;
   dim3 grid((L + q.stride - 1) / q.stride, n_seg);
-  kern<<<grid, 256, smem, st>>>(q);
+  kern<<<grid, NW * 32, smem, st>>>(q);
   post_launch("dec_last_kernel", st);
 }
 
@@ -338,9 +342,15 @@ bool dec_last_supported(int C, int cin, int up_k, int up_u, int nk, int nd, int 
 }
 
 void launch_dec_last(const DecStageParams& p, int C, int fmt, int n_seg, int max_len, cudaStream_t st) {
+  static const int nw = [] { const char* e = getenv("M3B200_DEC_WARPS"); return e ? atoi(e) : 16; }();
   if (C == 32) {
-    if (fmt) launch_dec_inst<32, 3, 1>(p, n_seg, max_len, st);
-    else launch_dec_inst<32, 3, 0>(p, n_seg, max_len, st);
+    if (nw == 8) {
+      if (fmt) launch_dec_inst<32, 3, 1, 8>(p, n_seg, max_len, st);
+      else launch_dec_inst<32, 3, 0, 8>(p, n_seg, max_len, st);
+    } else {
+      if (fmt) launch_dec_inst<32, 3, 1, 16>(p, n_seg, max_len, st);
+      else launch_dec_inst<32, 3, 0, 16>(p, n_seg, max_len, st);
+    }
   } else {
     throw std::runtime_error("dec_last: unsupported channel count");
   }

@@ -93,6 +93,34 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
 
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};\n" ::"r"(taddr),
+               "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+               "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])),
+               "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+               : "memory");
+}
+// G = 8 or 16 consecutive columns
+template <int G>
+__device__ __forceinline__ void tmem_ldg(uint32_t taddr, float* v) {
+  if constexpr (G == 16) tmem_ld16(taddr, v);
+  else tmem_ld8(taddr, v);
+}
+template <int G>
+__device__ __forceinline__ void tmem_stg(uint32_t taddr, const float* v) {
+  if constexpr (G == 16) tmem_st16(taddr, v);
+  else tmem_st8(taddr, v);
+}
+
 // ---- mbarrier ---------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -155,6 +183,12 @@ struct Elem<1> {  // bf16
     return *reinterpret_cast<uint32_t*>(&h);
   }
   static __host__ float round(float x) { return __bfloat162float(__float2bfloat16(x)); }
+  // leaky-relu on a packed pair: max(x, slope*x)  (slope < 1)
+  __device__ static __forceinline__ uint32_t lrelu2(uint32_t pk, float slope) {
+    const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&pk);
+    const __nv_bfloat162 r = __hmax2(h, __hmul2(h, __float2bfloat162_rn(slope)));
+    return *reinterpret_cast<const uint32_t*>(&r);
+  }
 };
 template <>
 struct Elem<0> {  // fp16
@@ -164,6 +198,11 @@ struct Elem<0> {  // fp16
     return *reinterpret_cast<uint32_t*>(&h);
   }
   static __host__ float round(float x) { return __half2float(__float2half(x)); }
+  __device__ static __forceinline__ uint32_t lrelu2(uint32_t pk, float slope) {
+    const __half2 h = *reinterpret_cast<const __half2*>(&pk);
+    const __half2 r = __hmax2(h, __hmul2(h, __float2half2_rn(slope)));
+    return *reinterpret_cast<const uint32_t*>(&r);
+  }
 };
 
 }  // namespace tc
