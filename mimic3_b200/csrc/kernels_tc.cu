@@ -355,7 +355,7 @@ void launch_mrf_tc(const MrfParams& p, int C, int fmt, int n_seg, int max_len, c
     else launch_mrf_inst<CC, NT, 0, NW, MINB>(q, n_seg, max_len, st);                     \
   }
   static const int nt32 = [] { const char* e = getenv("M3B200_MRF_NT32"); return e ? atoi(e) : 4; }();
-  static const int mrf_warps = [] { const char* e = getenv("M3B200_MRF_WARPS"); return e ? atoi(e) : 16; }();
+  static const int mrf_warps = [] { const char* e = getenv("M3B200_MRF_WARPS"); return e ? atoi(e) : 8; }();
   static const int nt64 = [] { const char* e = getenv("M3B200_MRF_NT64"); return e ? atoi(e) : 2; }();
   if (C == 32) {
     q.wg = pick_wg(16 * 1024);  // whole conv (<= 14 KB) per buffer; ~100 KB/CTA -> 2 CTAs/SM

@@ -342,7 +342,7 @@ bool dec_last_supported(int C, int cin, int up_k, int up_u, int nk, int nd, int 
 }
 
 void launch_dec_last(const DecStageParams& p, int C, int fmt, int n_seg, int max_len, cudaStream_t st) {
-  static const int nw = [] { const char* e = getenv("M3B200_DEC_WARPS"); return e ? atoi(e) : 16; }();
+  static const int nw = [] { const char* e = getenv("M3B200_DEC_WARPS"); return e ? atoi(e) : 8; }();  // 8 measured faster than 16 (profiles/r01_notes.md)
   if (C == 32) {
     if (nw == 8) {
       if (fmt) launch_dec_inst<32, 3, 1, 8>(p, n_seg, max_len, st);
