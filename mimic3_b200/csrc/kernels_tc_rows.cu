@@ -73,36 +73,53 @@ __global__ void __launch_bounds__(RG_THREADS, 2) rowgemm_tc_kernel(RowGemmTcPara
     // ===================== A stagers (then epilogue) =====================
     const int pad_left = p.pad_left;
     const int items = (RG_KB / 8) * RA;  // (row, 8-channel chunk) per stage, 128 threads
-    for (int kb = 0; kb < nkb; ++kb) {
-      const int s = kb % RG_STAGES;
-      tc::mbar_wait(&empty_bar[s], (((kb / RG_STAGES) & 1) ^ 1));
-      uint8_t* abuf = smem + size_t(s) * stage_bytes;
-      for (int idx = tid; idx < items; idx += 128) {
+    constexpr int MAXI = 5;              // items per thread: ceil(4 * 131 / 128)
+    // physical row of each of this thread's items (same for every K block)
+    int physr[MAXI], dsto[MAXI];
+#pragma unroll
+    for (int u = 0; u < MAXI; ++u) {
+      const int idx = tid + u * 128;
+      physr[u] = -2;  // no item
+      dsto[u] = 0;
+      if (idx < items) {
         const int rr = idx / (RG_KB / 8), c8 = idx - rr * (RG_KB / 8);
         const int v = v0 - pad_left + rr;
-        uint4 hi = make_uint4(0u, 0u, 0u, 0u), lo = hi;
-        if (v >= 0 && v < p.vrows) {
-          const int phys = p.vmap[v];
-          if (phys >= 0) {
-            const float* src = p.in + (long long)phys * p.in_stride + kb * RG_KB + c8 * 8;
-            const float4 a = *reinterpret_cast<const float4*>(src);
-            const float4 b = *reinterpret_cast<const float4*>(src + 4);
-            const float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-            uint32_t h[4], l[4];
+        physr[u] = (v >= 0 && v < p.vrows) ? p.vmap[v] : -1;
+        dsto[u] = c8 * RA + rr;
+      }
+    }
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % RG_STAGES;
+      // global loads first (all in flight together), THEN wait for the ring slot: the L2 latency of block
+      // kb overlaps the MMAs that are still draining the slot
+      float4 la[MAXI], lb[MAXI];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const __half2 hh = __floats2half2_rn(f[2 * e], f[2 * e + 1]);
-              const float2 back = __half22float2(hh);
-              const __half2 ll = __floats2half2_rn((f[2 * e] - back.x) * 2048.f, (f[2 * e + 1] - back.y) * 2048.f);
-              h[e] = *reinterpret_cast<const uint32_t*>(&hh);
-              l[e] = *reinterpret_cast<const uint32_t*>(&ll);
-            }
-            hi = make_uint4(h[0], h[1], h[2], h[3]);
-            lo = make_uint4(l[0], l[1], l[2], l[3]);
-          }
+      for (int u = 0; u < MAXI; ++u) {
+        la[u] = lb[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (physr[u] >= 0) {
+          const int c8 = dsto[u] / RA;
+          const float* src = p.in + (long long)physr[u] * p.in_stride + kb * RG_KB + c8 * 8;
+          la[u] = *reinterpret_cast<const float4*>(src);
+          lb[u] = *reinterpret_cast<const float4*>(src + 4);
         }
-        *reinterpret_cast<uint4*>(abuf + (size_t(c8) * RA + rr) * 16) = hi;
-        *reinterpret_cast<uint4*>(abuf + (size_t(RG_KB / 8 + c8) * RA + rr) * 16) = lo;
+      }
+      tc::mbar_wait(&empty_bar[s], (((kb / RG_STAGES) & 1) ^ 1));
+      uint8_t* abuf = smem + size_t(s) * stage_bytes;
+#pragma unroll
+      for (int u = 0; u < MAXI; ++u) {
+        if (physr[u] == -2) continue;
+        const float f[8] = {la[u].x, la[u].y, la[u].z, la[u].w, lb[u].x, lb[u].y, lb[u].z, lb[u].w};
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const __half2 hh = __floats2half2_rn(f[2 * e], f[2 * e + 1]);
+          const float2 back = __half22float2(hh);
+          const __half2 ll = __floats2half2_rn((f[2 * e] - back.x) * 2048.f, (f[2 * e + 1] - back.y) * 2048.f);
+          h[e] = *reinterpret_cast<const uint32_t*>(&hh);
+          l[e] = *reinterpret_cast<const uint32_t*>(&ll);
+        }
+        *reinterpret_cast<uint4*>(abuf + size_t(dsto[u]) * 16) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4*>(abuf + (size_t(RG_KB / 8) * RA + dsto[u]) * 16) = make_uint4(l[0], l[1], l[2], l[3]);
       }
       tc::fence_async_smem();
       __syncwarp();
