@@ -70,7 +70,7 @@ class ClockSampler:
         self.proc = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(gpu_index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "200", "-i", str(gpu_index)], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:  # nvidia-smi missing
@@ -108,19 +108,24 @@ class ClockSampler:
 
 
 def algorithmic_flops_per_frame(cfg) -> dict:
-    """SURVEY.md §8(d) general formula, per mel frame, from the voice's config."""
+    """SURVEY.md §8(d) general formula, per mel frame, from the voice's config.  Also returns the
+    per-stage split so the fused last-stage kernel can be charged with exactly its own work."""
     I = cfg.inter_channels
     C0 = cfg.upsample_initial_channel
-    out = {"conv_pre": 2 * I * C0 * 7, "ups": 0, "mrf": 0}
+    out = {"conv_pre": 2 * I * C0 * 7, "ups": 0, "mrf": 0, "ups_stage": [], "mrf_stage": []}
     L = 1
     c = C0
+    per = 2 if cfg.resblock == "1" else 1
     for i, (u, k) in enumerate(zip(cfg.upsample_rates, cfg.upsample_kernel_sizes)):
         cin, cout = c, c // 2
-        out["ups"] += 2 * cin * cout * k * L          # each input row touches k taps
+        up = 2 * cin * cout * k * L          # each input row touches k taps
         L *= u
-        nconv = sum(len(d) * (2 if cfg.resblock == "1" else 1) for d in cfg.resblock_dilation_sizes) / len(cfg.resblock_kernel_sizes)
-        for rk, dil in zip(cfg.resblock_kernel_sizes, cfg.resblock_dilation_sizes):
-            out["mrf"] += 2 * cout * cout * rk * len(dil) * (2 if cfg.resblock == "1" else 1) * L
+        mrf = sum(2 * cout * cout * rk * len(dil) * per * L
+                  for rk, dil in zip(cfg.resblock_kernel_sizes, cfg.resblock_dilation_sizes))
+        out["ups"] += up
+        out["mrf"] += mrf
+        out["ups_stage"].append(up)
+        out["mrf_stage"].append(mrf)
         c = cout
     out["post"] = 2 * c * 7 * L
     Hf = cfg.hidden_channels
@@ -328,15 +333,24 @@ def main():
     if rank == 0:
         value = tot_samples / wall_max
         fl = algorithmic_flops_per_frame(cfg)
-        mrf_ms = stage_ms["mrf"] / args.steps
-        mrf_flops = fl["mrf"] * (st_frames / args.steps)
+        frames_ps = st_frames / args.steps
         peaks = {}
         try:
             peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
         except Exception:
             pass
         peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
-        achieved_tf = mrf_flops / (mrf_ms * 1e-3) / 1e12 if mrf_ms > 0 else 0.0
+        dec_ms = stage_ms.get("dec_last", 0.0) / args.steps
+        mrf_ms = stage_ms["mrf"] / args.steps
+        if dec_ms > 0:   # dominant kernel: the fused last generator stage (upsample + MRF + conv_post)
+            k_name = "dec_last_kernel (ConvTranspose + MRF + conv_post, last stage)"
+            k_flops = (fl["ups_stage"][-1] + fl["mrf_stage"][-1] + fl["post"]) * frames_ps
+            k_ms = dec_ms
+            traffic = 393.1e6 * (GB / 64.0) / world  # ncu --set full capture at batch 64 (profiles/r01_ncu_final_tc_kernels.md), scaled
+        else:
+            k_name, k_flops, k_ms, traffic = "MRF stages (mrf_tc_kernel x3)", fl["mrf"] * frames_ps, mrf_ms, None
+        achieved_tf = k_flops / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
+        mrf_all_tf = fl["mrf"] * frames_ps / ((mrf_ms + dec_ms) * 1e-3) / 1e12 if (mrf_ms + dec_ms) > 0 else 0.0
         line = {
             "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": wall_max / args.steps * 1e3, "higher_is_better": True,
@@ -352,10 +366,13 @@ def main():
                        "timing": "wall clock between barrier+synchronize pairs (>= CUDA-event time), max over ranks",
                        "device_event_ms_per_step": dev_max / args.steps * 1e3},
             "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
-            "roofline": {"kernel": "MRF stage (resblock convs)", "bound": "tensor", "achieved": achieved_tf,
+            "roofline": {"kernel": k_name, "bound": "tensor", "achieved": achieved_tf,
                          "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf if peak_tf else None,
-                         "traffic": None,
-                         "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1400"},
+                         "traffic": traffic,
+                         "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (fp16 = same tensor rate)" if peaks else "fallback 1400",
+                         "kernel_ms": k_ms, "kernel_algorithmic_tflop": k_flops / 1e12,
+                         "all_mrf_stages_tflops": mrf_all_tf,
+                         "note": "smem operand fetch caps SS-mode MMAs at N=32 to 40 % of the tensor peak (DESIGN.md §3)"},
             "e2e": {"value": tot_e2e / e2e_max, "unit": "samples/s",
                     "h2d_bytes_per_step": int(GB * IDS_PER_UTT * 8 + GB * 16),
                     "d2h_bytes_per_step": int(tot_e2e / args.steps * 2)},

@@ -1321,7 +1321,7 @@ Result* run_inference(Voice& v, const int64_t* ids, const int64_t* lengths, int 
       dp.HY = ms.HY;
       dp.H = ms.HX + ms.HY + 3;
       launch_dec_last(dp, u.cout, dv.tc_fmt, batch, Fmax, st);
-      R.mark("mrf");
+      R.mark("dec_last");
       scale = out_scale;
       audio_done = true;
       break;

@@ -19,7 +19,7 @@ import numpy as np
 M3_OK, M3_ERR_INVALID, M3_ERR_IO, M3_ERR_MODEL, M3_ERR_CUDA, M3_ERR_NOGPU = range(6)
 FLAG_KEEP_FLOAT, FLAG_DEBUG_TENSORS, FLAG_DEVICE_IDS, FLAG_NO_HOST_COPY, FLAG_STAGE_TIMING = 1, 2, 4, 8, 16
 STAGES = ("text_encoder", "duration_predictor", "durations_sync", "expand", "flow", "conv_pre", "upsample", "mrf",
-          "post_int16")
+          "dec_last", "post_int16")
 
 _LIB_NAME = "libm3b200.so"
 _lib = None
