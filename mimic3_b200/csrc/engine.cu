@@ -651,6 +651,50 @@ std::unique_ptr<DeviceVoice> build_device_voice(const HostVoice& hv, int device)
             B.h16[o + ((size_t(tap) * (C / 8) + ci / 8) * 16 + 0) * 8 + (ci & 7)] = B.cvt16(pw.f32[size_t(ci) * 7 + tap]);
       }
       dv.dec_last.ok = true;
+
+      // ---- persistent fused kernel: every operand of the stage in one blob (polyphase transposed conv)
+      DecLastW& dl = dv.dec_last;
+      bool shape_ok = ms.nk == 3 && ms.nd == 2 && u.k == 2 * u.u;
+      if (shape_ok) {
+        for (int j = 0; j < 3; ++j) {
+          dl.HYb[j] = std::max(c.rb_dils[j][1] * (c.rb_kernels[j] - 1) / 2, j == 0 ? 3 : 0);
+        }
+        while (B.h16.size() % 64) B.h16.push_back(0);
+        dl.blob_off = B.h16.size();
+        auto here = [&] {
+          while (B.h16.size() % 64) B.h16.push_back(0);
+          return unsigned((B.h16.size() - dl.blob_off) * 2);
+        };
+        dl.f_up = here();
+        {
+          const int N = u.u * C;
+          const size_t o = B.h16.size();
+          B.h16.resize(o + size_t(2) * u.cin * N, 0);
+          for (int d = 0; d < 2; ++d)
+            for (int ci = 0; ci < u.cin; ++ci)
+              for (int ph = 0; ph < u.u; ++ph)
+                for (int co = 0; co < C; ++co)
+                  B.h16[o + ((size_t(d) * (u.cin / 8) + ci / 8) * N + ph * C + co) * 8 + (ci & 7)] =
+                      B.cvt16(w.f32[(size_t(ci) * u.cout + co) * u.k + (u.u * d + ph)]);
+        }
+        for (int j = 0; j < 3; ++j)
+          for (int d = 0; d < 2; ++d) {
+            const unsigned off = here();
+            (d == 0 ? dl.f_c1 : dl.f_c2)[j] = off;
+            const size_t n = size_t(c.rb_kernels[j]) * C * C;
+            const size_t src = ms.woff[j][d], o = B.h16.size();
+            B.h16.resize(o + n);
+            std::copy(B.h16.begin() + src, B.h16.begin() + src + n, B.h16.begin() + o);
+          }
+        dl.f_post = here();
+        {
+          const size_t n = size_t(7) * C * 16, src = dl.post_woff, o = B.h16.size();
+          B.h16.resize(o + n);
+          std::copy(B.h16.begin() + src, B.h16.begin() + src + n, B.h16.begin() + o);
+        }
+        dl.blob_bytes = here();
+        dl.fused_ok = dec_fused_supported(C, u.cin, u.k, u.u, ms.nk, ms.nd, ms.HX, dl.HYb, dl.blob_bytes);
+      }
     }
   }
 
@@ -1263,6 +1307,54 @@ Result* run_inference(Voice& v, const int64_t* ids, const int64_t* lengths, int 
   for (size_t i = 0; i < dv.ups.size(); ++i) {
     const UpW& u = dv.ups[i];
     const int out_scale = scale * u.u;
+    if (fuse_last && i + 1 == dv.ups.size() && dv.dec_last.fused_ok && !getenv("M3B200_DEC_V1")) {
+      const MrfStageW& ms = dv.mrf[i];
+      const DecLastW& dl = dv.dec_last;
+      DecFusedParams fp;
+      fp.yprev = cur;
+      fp.cin = u.cin;
+      fp.up_u = u.u;
+      fp.up_pad = u.pad;
+      fp.prev_scale = scale;
+      fp.scale = out_scale;
+      fp.audio = audio;
+      fp.peak_bits = peak;
+      fp.wblob = dv.slab16 + dl.blob_off;
+      fp.w_bytes = dl.blob_bytes;
+      fp.up.woff = dl.f_up;
+      fp.up.taps = 2;
+      fp.up.dil = -1;  // tap d reads y_prev row t - d
+      fp.up.pad_left = 0;
+      int hymax = 0;
+      for (int j = 0; j < 3; ++j) {
+        const ResBlockW& rb = dv.rbs[i * nk + j];
+        fp.c1[j].woff = dl.f_c1[j];
+        fp.c2[j].woff = dl.f_c2[j];
+        fp.c1[j].taps = fp.c2[j].taps = rb.k;
+        fp.c1[j].pad_left = fp.c2[j].pad_left = (rb.k - 1) / 2;
+        fp.c1[j].dil = rb.dil[0];
+        fp.c2[j].dil = rb.dil[1];
+        fp.bias1[j] = rb.c1[0].b;
+        fp.HYb[j] = dl.HYb[j];
+        hymax = std::max(hymax, dl.HYb[j]);
+      }
+      fp.post.woff = dl.f_post;
+      fp.post.taps = 7;
+      fp.post.dil = 1;
+      fp.post.pad_left = 3;
+      fp.up_bias = u.b;
+      fp.late_bias = ms.late_bias;
+      fp.inv_nk = 1.0f / float(ms.nk);
+      fp.seg_off = d_frm_off;
+      fp.seg_len = d_frm_len;
+      fp.HX = ms.HX;
+      fp.H = ms.HX + hymax + 3;
+      launch_dec_fused(fp, dv.tc_fmt, batch, Fmax, st);
+      R.mark("dec_last");
+      scale = out_scale;
+      audio_done = true;
+      break;
+    }
     if (fuse_last && i + 1 == dv.ups.size()) {
       const MrfStageW& ms = dv.mrf[i];
       DecStageParams dp;

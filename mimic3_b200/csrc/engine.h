@@ -100,6 +100,11 @@ struct MrfStageW {  // tensor-core packing of one MRF stage (kernels_tc.cu)
 struct DecLastW {  // fused last generator stage (kernels_tc_dec.cu)
   bool ok = false;
   unsigned long long up_woff = 0, post_woff = 0;
+  // persistent kernel (kernels_tc_dec2.cu): one contiguous blob, byte offsets relative to blob_off
+  bool fused_ok = false;
+  unsigned long long blob_off = 0;  // element offset in slab16
+  unsigned blob_bytes = 0, f_up = 0, f_post = 0, f_c1[3] = {}, f_c2[3] = {};
+  int HYb[3] = {};
 };
 
 struct DeviceVoice {

@@ -164,6 +164,35 @@ struct DecStageParams {
 bool dec_last_supported(int C, int cin, int up_k, int up_u, int nk, int nd, int HX, int HY);
 void launch_dec_last(const DecStageParams& p, int C, int fmt, int n_seg, int max_len, cudaStream_t st);
 
+// Persistent, warp-specialised version of the fused last stage (kernels_tc_dec2.cu).  All weights of the
+// stage live in ONE contiguous 16-bit blob (byte offsets below are relative to it):
+//   up   : polyphase transposed conv, per tap d in {0,1}: [cin/8][u*C][8], column ph*C+co = W[ci][co][u*d+ph]
+//   c1/c2: resblock j first / second conv, [tap][C/8][C][8]
+//   post : conv_post, [tap][C/8][16][8] (column 0 real)
+struct DecFusedConv {
+  unsigned woff = 0;
+  int taps = 1, dil = 1, pad_left = 0;
+};
+struct DecFusedParams {
+  const float* yprev = nullptr;  // [rows_prev][cin] fp32: previous stage output (pre-activation)
+  int cin = 0, up_u = 1, up_pad = 0, prev_scale = 1, scale = 1;
+  float* audio = nullptr;
+  unsigned* peak_bits = nullptr;
+  const uint16_t* wblob = nullptr;
+  unsigned w_bytes = 0;
+  DecFusedConv up, c1[3], c2[3], post;
+  const float* up_bias = nullptr;
+  const float* bias1[3] = {};
+  const float* late_bias = nullptr;
+  float inv_nk = 1.f;
+  const int* seg_off = nullptr;
+  const int* seg_len = nullptr;
+  int H = 0, HX = 0, HYb[3] = {};  // HYb: halo rows of resblock j's second-conv operand buffer (>= 3 for j = 0: conv_post reuses it)
+  int stride = 0, n_seg = 0, max_win = 0;  // filled by the launcher
+};
+bool dec_fused_supported(int C, int cin, int up_k, int up_u, int nk, int nd, int HX, const int* HYb, size_t w_bytes);
+void launch_dec_fused(const DecFusedParams& p, int fmt, int n_seg, int max_len, cudaStream_t st);
+
 // Fused coupling layer of the flow (kernels_tc_flow.cu).  Weights: one 16-bit stream in schedule order
 // (pre chunks | per layer: gate chunks x 5 taps, res chunks, skip chunks | post chunks), each stage
 // [K/8][64][8]; the channel Flip is folded into pre/post packing and x0_coff / x1_coff.

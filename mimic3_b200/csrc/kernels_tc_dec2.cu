@@ -1,0 +1,520 @@
+// Fused LAST stage of the HiFi-GAN generator, second generation: persistent + warp-specialised.
+//     x   = ConvTranspose1d(lrelu(y_prev, 0.1))                       (stride u, kernel k = 2u)
+//     out = 1/nk * sum_j ResBlock2_j(x)                               (MRF, nk = 3)
+//     y   = tanh(conv_post(lrelu(out, 0.01)))  (+ per-utterance max|y| for the int16 scaling)
+// (reference graph: the tail of generator.onnx run by
+//  mimic3_tts/voice.py:230.)  Differences to dec_last_kernel (kernels_tc_dec.cu):
+//   * one CTA per SM loops over (utterance, window) work items; ALL weights of the stage (~100 KB of
+//     fp16) are pulled into shared memory once per CTA with cp.async.bulk instead of once per window;
+//   * roles: warps 0-7 epilogue (TMEM -> registers -> activations back to smem), warp 8 issues every
+//     tcgen05.mma, warp 9 stages the next window's input; they only meet on mbarriers, so the tensor
+//     pipe runs resblock j+1 while the epilogue warps turn resblock j's accumulator into its next
+//     operand, and the next window's transposed conv / this window's conv_post fill the remaining gaps;
+//   * the transposed conv is POLYPHASE: D[t, ph*C+co] = sum_{d=0,1} lrelu(y[t-d]) . W[:, co, u*d+ph], one
+//     M=128 x N=u*C GEMM over y_prev rows -- no zero-stuffed rows, 1/7 of the MMA time.  Its output is
+//     transposed into sample order through an fp32 staging tile that aliases the (then idle) resblock
+//     operand buffers;
+//   * no running-sum round trips through TMEM: x and sum_j x1_j live in registers, all second convs
+//     accumulate into one TMEM tile S.
+// TMEM (512 columns): T_j = [96 j, 96 j + 96) conv1 accumulators, S = [288, 384) (conv_post reuses it),
+// D = [384, 512) transposed-conv result.
+#include <cstdlib>
+#include <stdexcept>
+#include <type_traits>
+
+#include "kernels.h"
+#include "tc_common.cuh"
+
+namespace m3 {
+
+namespace {
+constexpr int kC = 32, kNT = 3, kR = kNT * 128, kCH = kC / 8;
+constexpr int kEpiWarps = 8, kIssuer = 8, kLoader = 9, kThreads = 320;
+constexpr uint32_t kT0 = 0, kS0 = 288, kD0 = 384;
+enum Bar { W_FULL = 0, A_FULL, U_DONE, X_READY, C1_DONE, Y_READY = C1_DONE + 3, C2_DONE = Y_READY + 3, O_READY, P_DONE, NBAR };
+
+struct Geo {
+  int rows_x, rows_y[3], rows_a, nmu;
+  size_t off_w, off_x, off_y[3], off_a, total;
+};
+__host__ __device__ inline Geo make_geo(const DecFusedParams& p) {
+  Geo g;
+  g.rows_x = (kR + 2 * p.HX) | 1;
+  for (int j = 0; j < 3; ++j) g.rows_y[j] = (kR + 2 * p.HYb[j]) | 1;
+  g.nmu = (kR / p.up_u + 1 + 127) / 128;
+  g.rows_a = (g.nmu * 128 + 1) | 1;
+  size_t o = 0;
+  g.off_w = o;
+  o += (size_t(p.w_bytes) + 127) & ~size_t(127);
+  g.off_x = o;
+  o += size_t(kCH) * g.rows_x * 16;
+  for (int j = 0; j < 3; ++j) {
+    g.off_y[j] = o;
+    o += size_t(kCH) * g.rows_y[j] * 16;
+  }
+  g.off_a = o;
+  o += size_t(p.cin / 8) * g.rows_a * 16;
+  g.total = o;
+  return g;
+}
+
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;\n" ::: "memory"); }
+__device__ __forceinline__ float lrelu(float v, float s) { return fmaxf(v, s * v); }
+}  // namespace
+
+template <int FMT>
+__global__ void __launch_bounds__(kThreads, 1) dec_fused_kernel(DecFusedParams p) {
+  using E = tc::Elem<FMT>;
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint32_t tmem_slot;
+  __shared__ __align__(8) uint64_t bars[NBAR];
+  __shared__ __align__(16) float sbias[5][kC];  // [0] up bias, [1..3] first-conv bias of resblock j, [4] summed second-conv bias
+
+  const Geo g = make_geo(p);
+  uint8_t* const wts = smem + g.off_w;
+  uint8_t* const bufX = smem + g.off_x;
+  uint8_t* const bufA = smem + g.off_a;
+  uint8_t* const XS = smem + g.off_y[1];  // fp32 [kR][32] staging, aliases bufY1 + bufY2
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int u = p.up_u, CHI = p.cin / 8, NUP = u * kC;
+
+  // ---- work items: (utterance, window), the same deterministic sequence in every role ------------
+  const int total = p.n_seg * p.max_win;
+  auto valid = [&](int idx) {
+    const int seg = idx / p.max_win, win = idx - seg * p.max_win;
+    return win * p.stride < p.seg_len[seg] * p.scale;
+  };
+  auto next_item = [&](int idx) {
+    idx += int(gridDim.x);
+    while (idx < total && !valid(idx)) idx += int(gridDim.x);
+    return idx;
+  };
+  const int first = next_item(int(blockIdx.x) - int(gridDim.x));
+
+  // ---- one-time setup ----------------------------------------------------------------------------
+  if (tid == 0) {
+    for (int i = 0; i < NBAR; ++i) {
+      const bool many = i == X_READY || (i >= Y_READY && i < Y_READY + 3) || i == O_READY;
+      tc::mbar_init(&bars[i], many ? kEpiWarps : 1);
+    }
+    tc::mbar_fence_init();
+  }
+  for (int i = tid; i < 5 * kC; i += kThreads) {
+    const int j = i / kC, c = i - j * kC;
+    float v;
+    if (j == 0) v = p.up_bias[c];
+    else if (j <= 3) v = p.bias1[j - 1][c];
+    else v = p.late_bias[c];
+    sbias[j][c] = v;
+  }
+  {  // activations start as zeros: conv halos that no epilogue ever writes stay zero for the whole kernel
+    uint4* z = reinterpret_cast<uint4*>(smem + g.off_x);
+    const int n16 = int((g.total - g.off_x) / 16);
+    for (int i = tid; i < n16; i += kThreads) z[i] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  if (warp == kIssuer) tc::tmem_alloc<512>(&tmem_slot);
+  tc::fence_async_smem();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+
+  if (warp == kLoader) {
+    // =================================== loader warp ===============================================
+    if (first < total) {
+      if (tc::elect_one()) {
+        tc::mbar_expect_tx(&bars[W_FULL], p.w_bytes);
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wblob);
+        for (uint32_t o = 0; o < p.w_bytes; o += 32768u) {
+          const uint32_t n = p.w_bytes - o < 32768u ? p.w_bytes - o : 32768u;
+          tc::bulk_g2s(wts + o, src + o, n, &bars[W_FULL]);
+        }
+      }
+      __syncwarp();
+      const int rows_need = kR / u + 3 < g.rows_a ? kR / u + 3 : g.rows_a;
+      const int items = rows_need * CHI;
+      int it = 0;
+      for (int idx = first; idx < total; idx = next_item(idx), ++it) {
+        if (it > 0) tc::mbar_wait(&bars[U_DONE], uint32_t(it - 1) & 1u);  // previous window's transposed conv has read bufA
+        const int seg = idx / p.max_win, win = idx - seg * p.max_win;
+        const int Lprev = p.seg_len[seg] * p.prev_scale;
+        const long long base_prev = (long long)p.seg_off[seg] * p.prev_scale;
+        const int w0 = win * p.stride - p.H;
+        const int e = w0 + p.up_pad;
+        const int tq0 = e >= 0 ? e / u : -((-e + u - 1) / u);
+        for (int i0 = lane; i0 < items; i0 += 128) {
+          float4 a[4], b[4];
+          bool ok[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int i = i0 + 32 * k;
+            const int ra = i / CHI, c8 = i - ra * CHI;
+            const int t = tq0 - 1 + ra;
+            ok[k] = i < items && t >= 0 && t < Lprev;
+            if (ok[k]) {
+              const float4* src = reinterpret_cast<const float4*>(p.yprev + (base_prev + t) * (long long)p.cin + c8 * 8);
+              a[k] = __ldg(src);
+              b[k] = __ldg(src + 1);
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int i = i0 + 32 * k;
+            if (i >= items) continue;
+            const int ra = i / CHI, c8 = i - ra * CHI;
+            uint4 pk = make_uint4(0u, 0u, 0u, 0u);
+            if (ok[k]) {
+              pk.x = E::pack2(lrelu(a[k].x, 0.1f), lrelu(a[k].y, 0.1f));
+              pk.y = E::pack2(lrelu(a[k].z, 0.1f), lrelu(a[k].w, 0.1f));
+              pk.z = E::pack2(lrelu(b[k].x, 0.1f), lrelu(b[k].y, 0.1f));
+              pk.w = E::pack2(lrelu(b[k].z, 0.1f), lrelu(b[k].w, 0.1f));
+            }
+            *reinterpret_cast<uint4*>(bufA + (size_t(c8) * g.rows_a + ra) * 16) = pk;
+          }
+        }
+        tc::fence_async_smem();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&bars[A_FULL]);
+      }
+    }
+  } else if (warp == kIssuer) {
+    // =================================== MMA issuer warp ===========================================
+    if (first < total) {
+      const uint32_t wbase = tc::smem_u32(wts);
+      const uint32_t idC = tc::make_idesc(128, kC, FMT), idU = tc::make_idesc(128, NUP, FMT), idP = tc::make_idesc(128, 16, FMT);
+      // one conv = taps x (K/16) x ntile MMAs; a tap is a descriptor start-address shift.  The descriptors of
+      // one conv differ only in their 14-bit start-address field, so the (k-step, tile) grid of each tap is
+      // fully unrolled: independent address adds instead of a serial uniform-datapath loop per MMA
+      // (the rolled loop issued one MMA per ~100 cycles, 2.5x slower than the tensor pipe executes them).
+      auto issue = [&](auto ks_tag, auto nt_tag, uint32_t abase, int rows_in, int halo, const DecFusedConv& cv, int N,
+                       uint32_t dcol, int dstep, uint32_t idesc, bool acc0) {
+        constexpr int KS = decltype(ks_tag)::value, NTL = decltype(nt_tag)::value;
+        const uint64_t a_tmpl = tc::make_desc(0u, uint32_t(rows_in) * 16u, 128u);
+        const uint64_t b_tmpl = tc::make_desc(0u, uint32_t(N) * 16u, 128u);
+        const uint32_t a0 = (abase >> 4) + uint32_t(halo - cv.pad_left * cv.dil);
+        const uint32_t b0 = (wbase + cv.woff) >> 4;
+        const int bstep = 2 * KS * N;  // 16-byte units per tap: (K/8) * N
+#pragma unroll 1
+        for (int t = 0; t < cv.taps; ++t) {
+          const uint32_t at = a0 + uint32_t(t * cv.dil), bt = b0 + uint32_t(t * bstep);
+#pragma unroll
+          for (int ks = 0; ks < KS; ++ks) {
+            const uint64_t bd = b_tmpl | uint64_t((bt + uint32_t(ks * 2 * N)) & 0x3FFFu);
+            const uint32_t acc = (ks > 0 || acc0 || t > 0) ? 1u : 0u;
+#pragma unroll
+            for (int m = 0; m < NTL; ++m) {
+              const uint64_t ad = a_tmpl | uint64_t((at + uint32_t(ks * 2 * rows_in + m * 128)) & 0x3FFFu);
+              tc::mma_f16_ss(tmem + dcol + uint32_t(m * dstep), ad, bd, idesc, acc);
+            }
+          }
+        }
+      };
+      using I1 = std::integral_constant<int, 1>;
+      using I2 = std::integral_constant<int, 2>;
+      using I3 = std::integral_constant<int, 3>;
+      using I4 = std::integral_constant<int, 4>;
+      auto issue_up = [&] {  // K = cin (64 -> 4 k-steps, else generic), 1 or 2 row tiles
+        if (p.cin == 64 && g.nmu == 1) issue(I4{}, I1{}, tc::smem_u32(bufA), g.rows_a, 1, p.up, NUP, kD0, NUP, idU, false);
+        else if (p.cin == 64) issue(I4{}, I2{}, tc::smem_u32(bufA), g.rows_a, 1, p.up, NUP, kD0, NUP, idU, false);
+        else {
+          const uint64_t a_tmpl = tc::make_desc(0u, uint32_t(g.rows_a) * 16u, 128u);
+          const uint64_t b_tmpl = tc::make_desc(0u, uint32_t(NUP) * 16u, 128u);
+          for (int t = 0; t < p.up.taps; ++t)
+            for (int k0 = 0; k0 < p.cin / 16; ++k0)
+              for (int m = 0; m < g.nmu; ++m) {
+                const uint32_t a = (tc::smem_u32(bufA) >> 4) + uint32_t(1 - t + k0 * 2 * g.rows_a + m * 128);
+                const uint32_t b = ((wbase + p.up.woff) >> 4) + uint32_t((t * (p.cin / 8) + k0 * 2) * NUP);
+                tc::mma_f16_ss(tmem + kD0 + uint32_t(m * NUP), a_tmpl | uint64_t(a & 0x3FFFu), b_tmpl | uint64_t(b & 0x3FFFu), idU,
+                               (k0 || t) ? 1u : 0u);
+              }
+        }
+      };
+      const uint32_t aX = tc::smem_u32(bufX);
+      tc::mbar_wait(&bars[W_FULL], 0u);
+      tc::mbar_wait(&bars[A_FULL], 0u);
+      tc::fence_after_sync();
+      if (tc::elect_one()) {
+        issue_up();
+        tc::mma_commit(&bars[U_DONE]);
+      }
+      __syncwarp();
+      int it = 0;
+      for (int idx = first; idx < total; ++it) {
+        const int nxt = next_item(idx);
+        const uint32_t par = uint32_t(it) & 1u;
+        tc::mbar_wait(&bars[X_READY], par);
+        tc::fence_after_sync();
+        if (tc::elect_one()) {
+          for (int j = 0; j < 3; ++j) {
+            issue(I2{}, I3{}, aX, g.rows_x, p.HX, p.c1[j], kC, kT0 + uint32_t(j) * 96u, kC, idC, false);
+            tc::mma_commit(&bars[C1_DONE + j]);
+          }
+        }
+        __syncwarp();
+        for (int j = 0; j < 3; ++j) {
+          tc::mbar_wait(&bars[Y_READY + j], par);
+          tc::fence_after_sync();
+          if (tc::elect_one()) {
+            issue(I2{}, I3{}, tc::smem_u32(smem + g.off_y[j]), g.rows_y[j], p.HYb[j], p.c2[j], kC, kS0, kC, idC, j > 0);
+            if (j == 2) tc::mma_commit(&bars[C2_DONE]);
+          }
+          __syncwarp();
+        }
+        if (nxt < total) {  // next window's transposed conv fills the gap while the epilogue reduces this one
+          tc::mbar_wait(&bars[A_FULL], uint32_t(it + 1) & 1u);
+          tc::fence_after_sync();
+          if (tc::elect_one()) {
+            issue_up();
+            tc::mma_commit(&bars[U_DONE]);
+          }
+          __syncwarp();
+        }
+        tc::mbar_wait(&bars[O_READY], par);
+        tc::fence_after_sync();
+        if (tc::elect_one()) {
+          issue(I2{}, I3{}, tc::smem_u32(smem + g.off_y[0]), g.rows_y[0], p.HYb[0], p.post, 16, kS0, 16, idP, false);
+          tc::mma_commit(&bars[P_DONE]);
+        }
+        __syncwarp();
+        idx = nxt;
+      }
+    }
+  } else {
+    // =================================== epilogue warps ============================================
+    const int q = warp & 3, hhalf = warp >> 2;
+    const uint32_t lane_base = tmem + (uint32_t(q * 32) << 16);
+    const int col0 = hhalf * 16;
+    float xr[kNT][16], xs[kNT][16];
+
+    auto store_y = [&](uint8_t* buf, int pitch, int row, const uint32_t* pk) {  // 16 columns = 2 chunks of 8
+      uint8_t* dst = buf + (size_t(col0 / 8) * pitch + row) * 16;
+      *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      *reinterpret_cast<uint4*>(dst + size_t(pitch) * 16) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+    };
+    auto arrive = [&](int b) {
+      tc::fence_async_smem();
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&bars[b]);
+    };
+    auto post_epi = [&](int seg, int w0, int L, long long base, uint32_t par) {
+      tc::mbar_wait(&bars[P_DONE], par);
+      tc::fence_after_sync();
+      if (hhalf == 0) {
+        float mx = 0.f;
+#pragma unroll
+        for (int m = 0; m < kNT; ++m) {
+          float v[8];
+          tc::tmem_ld8(lane_base + kS0 + uint32_t(m * 16), v);
+          tc::tmem_ld_wait();
+          const int r = m * 128 + q * 32 + lane;
+          const int gi = w0 + r;
+          if (r >= p.H && r < kR - p.H && gi < L) {
+            const float y = tanhf(v[0]);
+            p.audio[base + gi] = y;
+            mx = fmaxf(mx, fabsf(y));
+          }
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if (lane == 0 && mx > 0.f) atomicMax(p.peak_bits + seg, __float_as_uint(mx));
+      }
+      tc::fence_before_sync();
+    };
+
+    int it = 0;
+    int pseg = 0, pw0 = 0, pL = 0;
+    long long pbase = 0;
+    for (int idx = first; idx < total; idx = next_item(idx), ++it) {
+      const uint32_t par = uint32_t(it) & 1u;
+      const int seg = idx / p.max_win, win = idx - seg * p.max_win;
+      const int L = p.seg_len[seg] * p.scale;
+      const long long base = (long long)p.seg_off[seg] * p.scale;
+      const int w0 = win * p.stride - p.H;
+      const int e = w0 + p.up_pad;
+      const int tq0 = e >= 0 ? e / u : -((-e + u - 1) / u);
+      const int ph0 = e - tq0 * u;
+
+      // ---- transposed-conv epilogue: D[t][ph*C + co] -> x in sample order ----
+      tc::mbar_wait(&bars[U_DONE], par);
+      tc::fence_after_sync();
+      for (int mt = 0; mt < g.nmu; ++mt) {
+        const int lq = mt * 128 + q * 32 + lane;
+        for (int pp = 0; pp < u / 2; ++pp) {
+          const int ph = hhalf * (u / 2) + pp;
+          float v[32];
+          tc::tmem_ld16(lane_base + kD0 + uint32_t(mt * NUP + ph * kC), v);
+          tc::tmem_ld16(lane_base + kD0 + uint32_t(mt * NUP + ph * kC + 16), v + 16);
+          tc::tmem_ld_wait();
+          const int r = u * lq + ph - ph0;
+          if (r >= 0 && r < kR) {
+            const int gi = w0 + r;
+            const bool inside = gi >= 0 && gi < L;
+            const int key = (r / u + r) & 7;
+            uint8_t* xrow = XS + size_t(r) * 128;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              float4 f;
+              f.x = v[4 * c] + sbias[0][4 * c];
+              f.y = v[4 * c + 1] + sbias[0][4 * c + 1];
+              f.z = v[4 * c + 2] + sbias[0][4 * c + 2];
+              f.w = v[4 * c + 3] + sbias[0][4 * c + 3];
+              v[4 * c] = f.x;
+              v[4 * c + 1] = f.y;
+              v[4 * c + 2] = f.z;
+              v[4 * c + 3] = f.w;
+              *reinterpret_cast<float4*>(xrow + ((c ^ key) << 4)) = f;
+            }
+#pragma unroll
+            for (int c8 = 0; c8 < 4; ++c8) {
+              uint4 pk = make_uint4(0u, 0u, 0u, 0u);
+              if (inside) {
+                pk.x = E::pack2(lrelu(v[8 * c8], 0.1f), lrelu(v[8 * c8 + 1], 0.1f));
+                pk.y = E::pack2(lrelu(v[8 * c8 + 2], 0.1f), lrelu(v[8 * c8 + 3], 0.1f));
+                pk.z = E::pack2(lrelu(v[8 * c8 + 4], 0.1f), lrelu(v[8 * c8 + 5], 0.1f));
+                pk.w = E::pack2(lrelu(v[8 * c8 + 6], 0.1f), lrelu(v[8 * c8 + 7], 0.1f));
+              }
+              *reinterpret_cast<uint4*>(bufX + (size_t(c8) * g.rows_x + r + p.HX) * 16) = pk;
+            }
+          }
+        }
+      }
+      arrive(X_READY);  // bufX is complete: the first convs may start while x is read back below
+      epi_bar();        // every x row is staged
+#pragma unroll
+      for (int m = 0; m < kNT; ++m) {
+        const int r = m * 128 + q * 32 + lane;
+        const int key = (r / u + r) & 7;
+        const uint8_t* xrow = XS + size_t(r) * 128;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float4 f = *reinterpret_cast<const float4*>(xrow + (((hhalf * 4 + c) ^ key) << 4));
+          xr[m][4 * c] = f.x;
+          xr[m][4 * c + 1] = f.y;
+          xr[m][4 * c + 2] = f.z;
+          xr[m][4 * c + 3] = f.w;
+        }
+      }
+      epi_bar();  // staging tile is dead: its bytes are bufY1 / bufY2 again
+      for (int j = 1; j < 3; ++j) {  // re-zero the halo rows the staging tile overwrote
+        uint8_t* by = smem + g.off_y[j];
+        const int hy = p.HYb[j], n = 2 * hy * kCH;
+        for (int i = tid; i < n; i += kEpiWarps * 32) {
+          const int c8 = i / (2 * hy), rr = i - c8 * 2 * hy;
+          const int row = rr < hy ? rr : kR + rr;  // [0, hy) and [kR + hy, kR + 2 hy)
+          *reinterpret_cast<uint4*>(by + (size_t(c8) * g.rows_y[j] + row) * 16) = make_uint4(0u, 0u, 0u, 0u);
+        }
+      }  // (made visible to the tensor pipe by the Y_READY arrivals below)
+
+      // ---- previous window's conv_post result (its MMAs ran during the code above) ----
+      if (it > 0) post_epi(pseg, pw0, pL, pbase, uint32_t(it - 1) & 1u);
+
+      // ---- first conv of each resblock: x1 = x + b + conv(lrelu x); operand of the second conv = lrelu(x1) ----
+#pragma unroll 1
+      for (int j = 0; j < 3; ++j) {
+        tc::mbar_wait(&bars[C1_DONE + j], par);
+        tc::fence_after_sync();
+        uint8_t* by = smem + g.off_y[j];
+        const int pitch = g.rows_y[j], hy = p.HYb[j];
+#pragma unroll
+        for (int m = 0; m < kNT; ++m) {
+          float v[16];
+          tc::tmem_ld16(lane_base + kT0 + uint32_t(j * 96 + m * kC + col0), v);
+          tc::tmem_ld_wait();
+          const int r = m * 128 + q * 32 + lane;
+          const int gi = w0 + r;
+          const bool inside = gi >= 0 && gi < L;
+          uint32_t pk[8];
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            v[c] += xr[m][c] + sbias[1 + j][col0 + c];
+            xs[m][c] = j == 0 ? v[c] : xs[m][c] + v[c];
+          }
+#pragma unroll
+          for (int c = 0; c < 8; ++c) pk[c] = inside ? E::pack2(lrelu(v[2 * c], 0.1f), lrelu(v[2 * c + 1], 0.1f)) : 0u;
+          store_y(by, pitch, r + hy, pk);
+        }
+        arrive(Y_READY + j);
+      }
+
+      // ---- out = (sum_j x1_j + S + late bias) / nk; operand of conv_post = lrelu(out, 0.01) in bufY0 ----
+      tc::mbar_wait(&bars[C2_DONE], par);
+      tc::fence_after_sync();
+      {
+        uint8_t* by = smem + g.off_y[0];
+        const int pitch = g.rows_y[0], hy = p.HYb[0];
+#pragma unroll
+        for (int m = 0; m < kNT; ++m) {
+          float v[16];
+          tc::tmem_ld16(lane_base + kS0 + uint32_t(m * kC + col0), v);
+          tc::tmem_ld_wait();
+          const int r = m * 128 + q * 32 + lane;
+          const int gi = w0 + r;
+          const bool inside = gi >= 0 && gi < L;
+          uint32_t pk[8];
+#pragma unroll
+          for (int c = 0; c < 16; ++c) v[c] = lrelu((v[c] + xs[m][c] + sbias[4][col0 + c]) * p.inv_nk, 0.01f);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) pk[c] = inside ? E::pack2(v[2 * c], v[2 * c + 1]) : 0u;
+          store_y(by, pitch, r + hy, pk);
+        }
+      }
+      arrive(O_READY);
+      pseg = seg;
+      pw0 = w0;
+      pL = L;
+      pbase = base;
+    }
+    if (it > 0) post_epi(pseg, pw0, pL, pbase, uint32_t(it - 1) & 1u);
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == kIssuer) tc::tmem_dealloc<512>(tmem);
+}
+
+size_t dec_fused_smem_bytes(const DecFusedParams& p) { return make_geo(p).total + 128; }
+
+bool dec_fused_supported(int C, int cin, int up_k, int up_u, int nk, int nd, int HX, const int* HYb, size_t w_bytes) {
+  if (C != kC || nk != 3 || nd != 2) return false;
+  if (cin % 16 || cin > 256 || up_u < 2 || (up_u & 1) || up_k != 2 * up_u) return false;
+  const int NUP = up_u * kC, nmu = (kR / up_u + 1 + 127) / 128;
+  if (NUP > 256 || nmu * NUP > 128) return false;  // TMEM columns [384, 512)
+  DecFusedParams p;
+  p.cin = cin;
+  p.up_u = up_u;
+  p.HX = HX;
+  for (int j = 0; j < 3; ++j) p.HYb[j] = HYb[j];
+  p.w_bytes = unsigned(w_bytes);
+  const Geo g = make_geo(p);
+  if (size_t(kCH) * (g.rows_y[1] + g.rows_y[2]) * 16 < size_t(kR) * 128) return false;  // fp32 staging alias
+  int HYmax = 0;
+  for (int j = 0; j < 3; ++j) HYmax = HYb[j] > HYmax ? HYb[j] : HYmax;
+  if (kR - 2 * (HX + HYmax + 3) < 64) return false;
+  return g.total + 128 + 1024 <= size_t(227) * 1024;
+}
+
+void launch_dec_fused(const DecFusedParams& p_in, int fmt, int n_seg, int max_len, cudaStream_t st) {
+  DecFusedParams p = p_in;
+  p.stride = kR - 2 * p.H;
+  if (p.stride <= 0) throw std::runtime_error("dec_fused: receptive field exceeds the window");
+  const int L = max_len * p.scale;
+  p.n_seg = n_seg;
+  p.max_win = (L + p.stride - 1) / p.stride;
+  if (p.max_win <= 0 || n_seg <= 0) return;
+  static const int n_sm = [] {
+    int dev = 0, n = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n;
+  }();
+  const size_t smem = dec_fused_smem_bytes(p);
+  const void* kern = fmt ? reinterpret_cast<const void*>(dec_fused_kernel<1>) : reinterpret_cast<const void*>(dec_fused_kernel<0>);
+  ensure_max_dynamic_smem(kern);
+  const long long items = (long long)n_seg * p.max_win;
+  const int grid = int(items < n_sm ? items : n_sm);
+  if (fmt) dec_fused_kernel<1><<<grid, kThreads, smem, st>>>(p);
+  else dec_fused_kernel<0><<<grid, kThreads, smem, st>>>(p);
+  post_launch("dec_fused_kernel", st);
+}
+
+}  // namespace m3

@@ -313,3 +313,40 @@ def test_text_side_tensor_core_split_keeps_durations(voices, built_library, monk
         np.testing.assert_array_equal(a.frames, b.frames)
     ref_s.close()
     tc_s.close()
+
+
+def test_persistent_last_stage_matches_per_window_kernel_and_oracle(voices, built_library, oracles, monkeypatch):
+    """The persistent warp-specialised last-stage kernel (polyphase transposed conv, kernels_tc_dec2.cu)
+    against the per-window fused kernel, the unfused kernels and the oracle, on a ragged batch that mixes
+    one-window utterances, many-window utterances and more work items than SMs."""
+    from mimic3_b200.engine import B200Session
+    rng = np.random.default_rng(77)
+    orc = oracles("low_ms")
+    lens_list = [1, 2, 5, 80, 33, 64] + [int(x) for x in rng.integers(3, 90, size=26)]
+    ids, lens = _batch(rng, 50, lens_list)
+    sid = rng.integers(0, 109, size=len(lens_list))
+    scales = (0.0, 1.0, 0.0)
+    sess = B200Session(str(voices("low_ms")))
+    got = sess.infer(ids, lens, scales, sid, keep_float=True)
+    again = sess.infer(ids, lens, scales, sid, keep_float=True)
+    monkeypatch.setenv("M3B200_DEC_V1", "1")
+    v1 = sess.infer(ids, lens, scales, sid, keep_float=True)
+    monkeypatch.delenv("M3B200_DEC_V1")
+    monkeypatch.setenv("M3B200_UNFUSED_DEC", "1")
+    unf = sess.infer(ids, lens, scales, sid, keep_float=True)
+    monkeypatch.delenv("M3B200_UNFUSED_DEC")
+    np.testing.assert_array_equal(got.frames, v1.frames)
+    np.testing.assert_array_equal(got.audio, again.audio)   # deterministic: no order-dependent accumulation
+    np.testing.assert_array_equal(got.peaks, again.peaks)
+    for other, name in ((v1, "per-window fused"), (unf, "unfused")):
+        for b in range(len(lens_list)):
+            a, c = got.utterance_audio(b), other.utterance_audio(b)
+            rms = float(np.sqrt(np.mean((a - c) ** 2)))
+            assert rms < 3e-4, (name, b, rms)
+            assert abs(float(got.peaks[b]) - float(np.abs(a).max())) == 0.0
+    for b in (0, 1, 2, 3, 10):
+        audio = orc.infer(ids[b, :lens[b]], scales, sid=int(sid[b]))
+        rms = float(np.sqrt(np.mean((got.utterance_audio(b) - audio) ** 2)))
+        print(f"utt {b} ({lens[b]} ids): RMS vs oracle {rms:.3e}")
+        assert rms <= RMS_TOL
+    sess.close()
