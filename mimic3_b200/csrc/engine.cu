@@ -1487,7 +1487,8 @@ Result* run_inference(Voice& v, const int64_t* ids, const int64_t* lengths, int 
       mp.HX = ms.HX;
       mp.HY = ms.HY;
       mp.inv_nk = 1.0f / float(ms.nk);
-      launch_mrf_tc(mp, u.cout, dv.tc_fmt, batch, Fmax, st);
+      if (!getenv("M3B200_MRF_V1") && mrf_ws_supported(mp, u.cout)) launch_mrf_ws(mp, dv.tc_fmt, batch, Fmax, st);
+      else launch_mrf_tc(mp, u.cout, dv.tc_fmt, batch, Fmax, st);
     } else
     for (int j = 0; j < nk; ++j) {
       const ResBlockW& rb = dv.rbs[i * nk + j];

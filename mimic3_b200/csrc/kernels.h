@@ -87,6 +87,7 @@ struct MrfParams {
   int wg = 1;      // taps per weight-staging group (launcher)
   float inv_nk = 1.f;
   int dbg = 0;     // M3B200_MRF_DEBUG bit mask (performance experiments only; breaks results)
+  int n_seg = 0, max_win = 0, nslot = 0;  // persistent kernel (kernels_tc_mrf2.cu), filled by its launcher
 };
 // Generic tensor-core Conv1d / polyphase ConvTranspose1d (kernels_tc.cu).
 // Weights: 16-bit, [chunk][tap][K/8][NC][8] (one contiguous block per (chunk, tap): a bulk copy).
@@ -214,6 +215,9 @@ bool flow_tc_supported(int Hc, int half, int nl, int kernel);
 void launch_flow_tc(const FlowTcParams& p, int fmt, int n_seg, int max_len, cudaStream_t st);
 
 bool mrf_tc_supported(int C, int nk, int nd, const int* k, int max_halo);
+// persistent warp-specialised variant for C = 64, three ResBlock2 chains (kernels_tc_mrf2.cu)
+bool mrf_ws_supported(const MrfParams& p, int C);
+void launch_mrf_ws(const MrfParams& p, int fmt, int n_seg, int max_len, cudaStream_t st);
 // fmt: 0 = fp16 operands, 1 = bf16 operands
 void launch_mrf_tc(const MrfParams& p, int C, int fmt, int n_seg, int max_len, cudaStream_t st);
 

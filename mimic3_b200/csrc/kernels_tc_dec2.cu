@@ -7,7 +7,7 @@
 //   * one CTA per SM loops over (utterance, window) work items; ALL weights of the stage (~100 KB of
 //     fp16) are pulled into shared memory once per CTA with cp.async.bulk instead of once per window;
 //   * roles: warps 0-7 epilogue (TMEM -> registers -> activations back to smem), warp 8 issues every
-//     tcgen05.mma, warp 9 stages the next window's input; they only meet on mbarriers, so the tensor
+//     tcgen05.mma, warps 9-11 stage the next window's input; they only meet on mbarriers, so the tensor
 //     pipe runs resblock j+1 while the epilogue warps turn resblock j's accumulator into its next
 //     operand, and the next window's transposed conv / this window's conv_post fill the remaining gaps;
 //   * the transposed conv is POLYPHASE: D[t, ph*C+co] = sum_{d=0,1} lrelu(y[t-d]) . W[:, co, u*d+ph], one
@@ -29,7 +29,8 @@ namespace m3 {
 
 namespace {
 constexpr int kC = 32, kNT = 3, kR = kNT * 128, kCH = kC / 8;
-constexpr int kEpiWarps = 8, kIssuer = 8, kLoader = 9, kThreads = 320;
+constexpr int kEpiWarps = 8, kIssuer = 8, kLoader = 9, kLoaders = 3, kThreads = 32 * (kLoader + kLoaders);
+constexpr int kLoadDepth = 9;   // y_prev rows-chunks in flight per loader lane (one round for u = 4)
 constexpr uint32_t kT0 = 0, kS0 = 288, kD0 = 384;
 enum Bar { W_FULL = 0, A_FULL, U_DONE, X_READY, C1_DONE, Y_READY = C1_DONE + 3, C2_DONE = Y_READY + 3, O_READY, P_DONE, NBAR };
 
@@ -95,7 +96,7 @@ __global__ void __launch_bounds__(kThreads, 1) dec_fused_kernel(DecFusedParams p
   if (tid == 0) {
     for (int i = 0; i < NBAR; ++i) {
       const bool many = i == X_READY || (i >= Y_READY && i < Y_READY + 3) || i == O_READY;
-      tc::mbar_init(&bars[i], many ? kEpiWarps : 1);
+      tc::mbar_init(&bars[i], many ? kEpiWarps : (i == A_FULL ? kLoaders : 1));
     }
     tc::mbar_fence_init();
   }
@@ -119,10 +120,10 @@ __global__ void __launch_bounds__(kThreads, 1) dec_fused_kernel(DecFusedParams p
   tc::fence_after_sync();
   const uint32_t tmem = tmem_slot;
 
-  if (warp == kLoader) {
+  if (warp >= kLoader) {
     // =================================== loader warp ===============================================
     if (first < total) {
-      if (tc::elect_one()) {
+      if (warp == kLoader && tc::elect_one()) {
         tc::mbar_expect_tx(&bars[W_FULL], p.w_bytes);
         const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wblob);
         for (uint32_t o = 0; o < p.w_bytes; o += 32768u) {
@@ -142,12 +143,13 @@ __global__ void __launch_bounds__(kThreads, 1) dec_fused_kernel(DecFusedParams p
         const int w0 = win * p.stride - p.H;
         const int e = w0 + p.up_pad;
         const int tq0 = e >= 0 ? e / u : -((-e + u - 1) / u);
-        for (int i0 = lane; i0 < items; i0 += 128) {
-          float4 a[4], b[4];
-          bool ok[4];
+        const int lt = (warp - kLoader) * 32 + lane;
+        for (int i0 = lt; i0 < items; i0 += 32 * kLoaders * kLoadDepth) {  // all global loads of a round in flight together
+          float4 a[kLoadDepth], b[kLoadDepth];
+          bool ok[kLoadDepth];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int i = i0 + 32 * k;
+          for (int k = 0; k < kLoadDepth; ++k) {
+            const int i = i0 + 32 * kLoaders * k;
             const int ra = i / CHI, c8 = i - ra * CHI;
             const int t = tq0 - 1 + ra;
             ok[k] = i < items && t >= 0 && t < Lprev;
@@ -158,8 +160,8 @@ __global__ void __launch_bounds__(kThreads, 1) dec_fused_kernel(DecFusedParams p
             }
           }
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int i = i0 + 32 * k;
+          for (int k = 0; k < kLoadDepth; ++k) {
+            const int i = i0 + 32 * kLoaders * k;
             if (i >= items) continue;
             const int ra = i / CHI, c8 = i - ra * CHI;
             uint4 pk = make_uint4(0u, 0u, 0u, 0u);
@@ -336,6 +338,8 @@ __global__ void __launch_bounds__(kThreads, 1) dec_fused_kernel(DecFusedParams p
       const int ph0 = e - tq0 * u;
 
       // ---- transposed-conv epilogue: D[t][ph*C + co] -> x in sample order ----
+      // pass 1 (lane = y_prev row): x = D + b into the fp32 staging tile, 16-byte chunks XOR-swizzled so that
+      // both this strided write (rows u apart) and the row-per-lane read below are bank-conflict free
       tc::mbar_wait(&bars[U_DONE], par);
       tc::fence_after_sync();
       for (int mt = 0; mt < g.nmu; ++mt) {
@@ -348,43 +352,31 @@ __global__ void __launch_bounds__(kThreads, 1) dec_fused_kernel(DecFusedParams p
           tc::tmem_ld_wait();
           const int r = u * lq + ph - ph0;
           if (r >= 0 && r < kR) {
-            const int gi = w0 + r;
-            const bool inside = gi >= 0 && gi < L;
-            const int key = (r / u + r) & 7;
+            const int key = (r & 7) ^ ((r >> 3) & 3);
             uint8_t* xrow = XS + size_t(r) * 128;
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
+              const float4 bb = *reinterpret_cast<const float4*>(&sbias[0][4 * c]);
               float4 f;
-              f.x = v[4 * c] + sbias[0][4 * c];
-              f.y = v[4 * c + 1] + sbias[0][4 * c + 1];
-              f.z = v[4 * c + 2] + sbias[0][4 * c + 2];
-              f.w = v[4 * c + 3] + sbias[0][4 * c + 3];
-              v[4 * c] = f.x;
-              v[4 * c + 1] = f.y;
-              v[4 * c + 2] = f.z;
-              v[4 * c + 3] = f.w;
+              f.x = v[4 * c] + bb.x;
+              f.y = v[4 * c + 1] + bb.y;
+              f.z = v[4 * c + 2] + bb.z;
+              f.w = v[4 * c + 3] + bb.w;
               *reinterpret_cast<float4*>(xrow + ((c ^ key) << 4)) = f;
-            }
-#pragma unroll
-            for (int c8 = 0; c8 < 4; ++c8) {
-              uint4 pk = make_uint4(0u, 0u, 0u, 0u);
-              if (inside) {
-                pk.x = E::pack2(lrelu(v[8 * c8], 0.1f), lrelu(v[8 * c8 + 1], 0.1f));
-                pk.y = E::pack2(lrelu(v[8 * c8 + 2], 0.1f), lrelu(v[8 * c8 + 3], 0.1f));
-                pk.z = E::pack2(lrelu(v[8 * c8 + 4], 0.1f), lrelu(v[8 * c8 + 5], 0.1f));
-                pk.w = E::pack2(lrelu(v[8 * c8 + 6], 0.1f), lrelu(v[8 * c8 + 7], 0.1f));
-              }
-              *reinterpret_cast<uint4*>(bufX + (size_t(c8) * g.rows_x + r + p.HX) * 16) = pk;
             }
           }
         }
       }
-      arrive(X_READY);  // bufX is complete: the first convs may start while x is read back below
-      epi_bar();        // every x row is staged
+      tc::fence_before_sync();
+      epi_bar();  // every x row is staged
+      // pass 2 (lane = sample row, as in every later epilogue): keep x in registers, publish lrelu(x) as the
+      // first convs' operand
 #pragma unroll
       for (int m = 0; m < kNT; ++m) {
         const int r = m * 128 + q * 32 + lane;
-        const int key = (r / u + r) & 7;
+        const int gi = w0 + r;
+        const bool inside = gi >= 0 && gi < L;
+        const int key = (r & 7) ^ ((r >> 3) & 3);
         const uint8_t* xrow = XS + size_t(r) * 128;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -394,7 +386,12 @@ __global__ void __launch_bounds__(kThreads, 1) dec_fused_kernel(DecFusedParams p
           xr[m][4 * c + 2] = f.z;
           xr[m][4 * c + 3] = f.w;
         }
+        uint32_t pk[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) pk[c] = inside ? E::pack2(lrelu(xr[m][2 * c], 0.1f), lrelu(xr[m][2 * c + 1], 0.1f)) : 0u;
+        store_y(bufX, g.rows_x, r + p.HX, pk);
       }
+      arrive(X_READY);
       epi_bar();  // staging tile is dead: its bytes are bufY1 / bufY2 again
       for (int j = 1; j < 3; ++j) {  // re-zero the halo rows the staging tile overwrote
         uint8_t* by = smem + g.off_y[j];
@@ -416,6 +413,15 @@ __global__ void __launch_bounds__(kThreads, 1) dec_fused_kernel(DecFusedParams p
         tc::fence_after_sync();
         uint8_t* by = smem + g.off_y[j];
         const int pitch = g.rows_y[j], hy = p.HYb[j];
+        float bj[16];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float4 f = *reinterpret_cast<const float4*>(&sbias[1 + j][col0 + 4 * c]);
+          bj[4 * c] = f.x;
+          bj[4 * c + 1] = f.y;
+          bj[4 * c + 2] = f.z;
+          bj[4 * c + 3] = f.w;
+        }
 #pragma unroll
         for (int m = 0; m < kNT; ++m) {
           float v[16];
@@ -427,7 +433,7 @@ __global__ void __launch_bounds__(kThreads, 1) dec_fused_kernel(DecFusedParams p
           uint32_t pk[8];
 #pragma unroll
           for (int c = 0; c < 16; ++c) {
-            v[c] += xr[m][c] + sbias[1 + j][col0 + c];
+            v[c] += xr[m][c] + bj[c];
             xs[m][c] = j == 0 ? v[c] : xs[m][c] + v[c];
           }
 #pragma unroll
@@ -443,6 +449,15 @@ __global__ void __launch_bounds__(kThreads, 1) dec_fused_kernel(DecFusedParams p
       {
         uint8_t* by = smem + g.off_y[0];
         const int pitch = g.rows_y[0], hy = p.HYb[0];
+        float bl[16];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float4 f = *reinterpret_cast<const float4*>(&sbias[4][col0 + 4 * c]);
+          bl[4 * c] = f.x;
+          bl[4 * c + 1] = f.y;
+          bl[4 * c + 2] = f.z;
+          bl[4 * c + 3] = f.w;
+        }
 #pragma unroll
         for (int m = 0; m < kNT; ++m) {
           float v[16];
@@ -453,7 +468,7 @@ __global__ void __launch_bounds__(kThreads, 1) dec_fused_kernel(DecFusedParams p
           const bool inside = gi >= 0 && gi < L;
           uint32_t pk[8];
 #pragma unroll
-          for (int c = 0; c < 16; ++c) v[c] = lrelu((v[c] + xs[m][c] + sbias[4][col0 + c]) * p.inv_nk, 0.01f);
+          for (int c = 0; c < 16; ++c) v[c] = lrelu((v[c] + xs[m][c] + bl[c]) * p.inv_nk, 0.01f);
 #pragma unroll
           for (int c = 0; c < 8; ++c) pk[c] = inside ? E::pack2(v[2 * c], v[2 * c + 1]) : 0u;
           store_y(by, pitch, r + hy, pk);

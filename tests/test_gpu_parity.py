@@ -335,10 +335,13 @@ def test_persistent_last_stage_matches_per_window_kernel_and_oracle(voices, buil
     monkeypatch.setenv("M3B200_UNFUSED_DEC", "1")
     unf = sess.infer(ids, lens, scales, sid, keep_float=True)
     monkeypatch.delenv("M3B200_UNFUSED_DEC")
+    monkeypatch.setenv("M3B200_MRF_V1", "1")   # per-window MRF kernel for the C = 64 stage instead of the persistent one
+    mrf_v1 = sess.infer(ids, lens, scales, sid, keep_float=True)
+    monkeypatch.delenv("M3B200_MRF_V1")
     np.testing.assert_array_equal(got.frames, v1.frames)
     np.testing.assert_array_equal(got.audio, again.audio)   # deterministic: no order-dependent accumulation
     np.testing.assert_array_equal(got.peaks, again.peaks)
-    for other, name in ((v1, "per-window fused"), (unf, "unfused")):
+    for other, name in ((v1, "per-window fused"), (unf, "unfused"), (mrf_v1, "per-window MRF")):
         for b in range(len(lens_list)):
             a, c = got.utterance_audio(b), other.utterance_audio(b)
             rms = float(np.sqrt(np.mean((a - c) ** 2)))
