@@ -88,6 +88,7 @@ struct MrfParams {
   float inv_nk = 1.f;
   int dbg = 0;     // M3B200_MRF_DEBUG bit mask (performance experiments only; breaks results)
   int n_seg = 0, max_win = 0, nslot = 0;  // persistent kernel (kernels_tc_mrf2.cu), filled by its launcher
+  long long* prof = nullptr;              // M3B200_MRF_PROFILE=1: per-role cycle counters (debug)
 };
 // Generic tensor-core Conv1d / polyphase ConvTranspose1d (kernels_tc.cu).
 // Weights: 16-bit, [chunk][tap][K/8][NC][8] (one contiguous block per (chunk, tap): a bulk copy).

@@ -32,6 +32,7 @@ constexpr int kC = 32, kNT = 3, kR = kNT * 128, kCH = kC / 8;
 constexpr int kEpiWarps = 8, kIssuer = 8, kLoader = 9, kLoaders = 3, kThreads = 32 * (kLoader + kLoaders);
 constexpr int kLoadDepth = 9;   // y_prev rows-chunks in flight per loader lane (one round for u = 4)
 constexpr uint32_t kT0 = 0, kS0 = 288, kD0 = 384;
+constexpr int kSegTable = 1024;
 enum Bar { W_FULL = 0, A_FULL, U_DONE, X_READY, C1_DONE, Y_READY = C1_DONE + 3, C2_DONE = Y_READY + 3, O_READY, P_DONE, NBAR };
 
 struct Geo {
@@ -80,10 +81,14 @@ __global__ void __launch_bounds__(kThreads, 1) dec_fused_kernel(DecFusedParams p
   const int u = p.up_u, CHI = p.cin / 8, NUP = u * kC;
 
   // ---- work items: (utterance, window), the same deterministic sequence in every role ------------
+  __shared__ int s_rows[kSegTable];  // per-utterance sample counts (larger batches fall back to global memory)
+  auto seg_rows = [&](int seg) { return seg < kSegTable ? s_rows[seg] : p.seg_len[seg] * p.scale; };
+  for (int i = threadIdx.x; i < p.n_seg && i < kSegTable; i += kThreads) s_rows[i] = p.seg_len[i] * p.scale;
+  __syncthreads();
   const int total = p.n_seg * p.max_win;
   auto valid = [&](int idx) {
     const int seg = idx / p.max_win, win = idx - seg * p.max_win;
-    return win * p.stride < p.seg_len[seg] * p.scale;
+    return win * p.stride < seg_rows(seg);
   };
   auto next_item = [&](int idx) {
     idx += int(gridDim.x);
@@ -138,7 +143,7 @@ __global__ void __launch_bounds__(kThreads, 1) dec_fused_kernel(DecFusedParams p
       for (int idx = first; idx < total; idx = next_item(idx), ++it) {
         if (it > 0) tc::mbar_wait(&bars[U_DONE], uint32_t(it - 1) & 1u);  // previous window's transposed conv has read bufA
         const int seg = idx / p.max_win, win = idx - seg * p.max_win;
-        const int Lprev = p.seg_len[seg] * p.prev_scale;
+        const int Lprev = seg_rows(seg) / p.scale * p.prev_scale;
         const long long base_prev = (long long)p.seg_off[seg] * p.prev_scale;
         const int w0 = win * p.stride - p.H;
         const int e = w0 + p.up_pad;
@@ -191,21 +196,21 @@ __global__ void __launch_bounds__(kThreads, 1) dec_fused_kernel(DecFusedParams p
       auto issue = [&](auto ks_tag, auto nt_tag, uint32_t abase, int rows_in, int halo, const DecFusedConv& cv, int N,
                        uint32_t dcol, int dstep, uint32_t idesc, bool acc0) {
         constexpr int KS = decltype(ks_tag)::value, NTL = decltype(nt_tag)::value;
-        const uint64_t a_tmpl = tc::make_desc(0u, uint32_t(rows_in) * 16u, 128u);
-        const uint64_t b_tmpl = tc::make_desc(0u, uint32_t(N) * 16u, 128u);
-        const uint32_t a0 = (abase >> 4) + uint32_t(halo - cv.pad_left * cv.dil);
-        const uint32_t b0 = (wbase + cv.woff) >> 4;
-        const int bstep = 2 * KS * N;  // 16-byte units per tap: (K/8) * N
+        const uint64_t a_tmpl = tc::make_desc(abase, uint32_t(rows_in) * 16u, 128u);
+        const uint64_t b_tmpl = tc::make_desc(wbase + cv.woff, uint32_t(N) * 16u, 128u);
+        const uint32_t a_hi = uint32_t(a_tmpl >> 32), b_hi = uint32_t(b_tmpl >> 32);
+        uint32_t at = uint32_t(a_tmpl) + uint32_t(halo - cv.pad_left * cv.dil), bt = uint32_t(b_tmpl);
+        const uint32_t bstep = uint32_t(2 * KS * N);  // 16-byte units per tap: (K/8) * N
+        const uint32_t kstep = uint32_t(2 * rows_in);
 #pragma unroll 1
-        for (int t = 0; t < cv.taps; ++t) {
-          const uint32_t at = a0 + uint32_t(t * cv.dil), bt = b0 + uint32_t(t * bstep);
+        for (int t = 0; t < cv.taps; ++t, at += uint32_t(cv.dil), bt += bstep) {
 #pragma unroll
           for (int ks = 0; ks < KS; ++ks) {
-            const uint64_t bd = b_tmpl | uint64_t((bt + uint32_t(ks * 2 * N)) & 0x3FFFu);
+            const uint64_t bd = (uint64_t(b_hi) << 32) | uint64_t(bt + uint32_t(ks * 2 * N));
             const uint32_t acc = (ks > 0 || acc0 || t > 0) ? 1u : 0u;
 #pragma unroll
             for (int m = 0; m < NTL; ++m) {
-              const uint64_t ad = a_tmpl | uint64_t((at + uint32_t(ks * 2 * rows_in + m * 128)) & 0x3FFFu);
+              const uint64_t ad = (uint64_t(a_hi) << 32) | uint64_t(at + uint32_t(ks) * kstep + uint32_t(m * 128));
               tc::mma_f16_ss(tmem + dcol + uint32_t(m * dstep), ad, bd, idesc, acc);
             }
           }
@@ -232,54 +237,43 @@ __global__ void __launch_bounds__(kThreads, 1) dec_fused_kernel(DecFusedParams p
         }
       };
       const uint32_t aX = tc::smem_u32(bufX);
-      tc::mbar_wait(&bars[W_FULL], 0u);
-      tc::mbar_wait(&bars[A_FULL], 0u);
-      tc::fence_after_sync();
+      // ONE elected thread runs the whole schedule, waits included: no warp reconvergence between convs
       if (tc::elect_one()) {
+        tc::mbar_wait(&bars[W_FULL], 0u);
+        tc::mbar_wait(&bars[A_FULL], 0u);
+        tc::fence_after_sync();
         issue_up();
         tc::mma_commit(&bars[U_DONE]);
-      }
-      __syncwarp();
-      int it = 0;
-      for (int idx = first; idx < total; ++it) {
-        const int nxt = next_item(idx);
-        const uint32_t par = uint32_t(it) & 1u;
-        tc::mbar_wait(&bars[X_READY], par);
-        tc::fence_after_sync();
-        if (tc::elect_one()) {
+        int it = 0;
+        for (int idx = first; idx < total; ++it) {
+          const int nxt = next_item(idx);
+          const uint32_t par = uint32_t(it) & 1u;
+          tc::mbar_wait(&bars[X_READY], par);
+          tc::fence_after_sync();
           for (int j = 0; j < 3; ++j) {
             issue(I2{}, I3{}, aX, g.rows_x, p.HX, p.c1[j], kC, kT0 + uint32_t(j) * 96u, kC, idC, false);
             tc::mma_commit(&bars[C1_DONE + j]);
           }
-        }
-        __syncwarp();
-        for (int j = 0; j < 3; ++j) {
-          tc::mbar_wait(&bars[Y_READY + j], par);
-          tc::fence_after_sync();
-          if (tc::elect_one()) {
+          for (int j = 0; j < 3; ++j) {
+            tc::mbar_wait(&bars[Y_READY + j], par);
+            tc::fence_after_sync();
             issue(I2{}, I3{}, tc::smem_u32(smem + g.off_y[j]), g.rows_y[j], p.HYb[j], p.c2[j], kC, kS0, kC, idC, j > 0);
-            if (j == 2) tc::mma_commit(&bars[C2_DONE]);
           }
-          __syncwarp();
-        }
-        if (nxt < total) {  // next window's transposed conv fills the gap while the epilogue reduces this one
-          tc::mbar_wait(&bars[A_FULL], uint32_t(it + 1) & 1u);
-          tc::fence_after_sync();
-          if (tc::elect_one()) {
+          tc::mma_commit(&bars[C2_DONE]);
+          if (nxt < total) {  // next window's transposed conv fills the gap while the epilogue reduces this one
+            tc::mbar_wait(&bars[A_FULL], uint32_t(it + 1) & 1u);
+            tc::fence_after_sync();
             issue_up();
             tc::mma_commit(&bars[U_DONE]);
           }
-          __syncwarp();
-        }
-        tc::mbar_wait(&bars[O_READY], par);
-        tc::fence_after_sync();
-        if (tc::elect_one()) {
+          tc::mbar_wait(&bars[O_READY], par);
+          tc::fence_after_sync();
           issue(I2{}, I3{}, tc::smem_u32(smem + g.off_y[0]), g.rows_y[0], p.HYb[0], p.post, 16, kS0, 16, idP, false);
           tc::mma_commit(&bars[P_DONE]);
+          idx = nxt;
         }
-        __syncwarp();
-        idx = nxt;
       }
+      __syncwarp();
     }
   } else {
     // =================================== epilogue warps ============================================
@@ -330,7 +324,7 @@ __global__ void __launch_bounds__(kThreads, 1) dec_fused_kernel(DecFusedParams p
     for (int idx = first; idx < total; idx = next_item(idx), ++it) {
       const uint32_t par = uint32_t(it) & 1u;
       const int seg = idx / p.max_win, win = idx - seg * p.max_win;
-      const int L = p.seg_len[seg] * p.scale;
+      const int L = seg_rows(seg);
       const long long base = (long long)p.seg_off[seg] * p.scale;
       const int w0 = win * p.stride - p.H;
       const int e = w0 + p.up_pad;
@@ -505,7 +499,7 @@ bool dec_fused_supported(int C, int cin, int up_k, int up_u, int nk, int nd, int
   int HYmax = 0;
   for (int j = 0; j < 3; ++j) HYmax = HYb[j] > HYmax ? HYb[j] : HYmax;
   if (kR - 2 * (HX + HYmax + 3) < 64) return false;
-  return g.total + 128 + 1024 <= size_t(227) * 1024;
+  return g.total + 128 + 1024 + 4 * kSegTable <= size_t(227) * 1024;
 }
 
 void launch_dec_fused(const DecFusedParams& p_in, int fmt, int n_seg, int max_len, cudaStream_t st) {

@@ -2,8 +2,8 @@
 // persistent + warp-specialised.  Same math as mrf_tc_kernel (kernels_tc.cu):
 //     out = 1/nk * sum_j [ x1_j + conv2_j(lrelu(x1_j)) ],   x1_j = x + conv1_j(lrelu(x))
 // but organised like dec_fused_kernel (kernels_tc_dec2.cu):
-//   * one CTA per SM loops over (utterance, window) items; warps 0-15 are epilogue warps, warp 16 issues
-//     every tcgen05.mma, warp 17 streams the weights tap by tap (8 KB cp.async.bulk blocks, L2-resident)
+//   * one CTA per SM loops over (utterance, window) items; warps 0-7 are epilogue warps, warps 8-9 issue
+//     the tcgen05.mma of one 128-row tile each, warp 10 streams the weights tap by tap (8 KB cp.async.bulk blocks, L2-resident)
 //     through a ring of shared-memory slots guarded by full/empty mbarriers;
 //   * the three resblocks are independent chains: the tensor pipe runs conv1 of chain j+1 while the
 //     epilogue warps turn chain j's accumulator into its second conv's operand, and all second convs
@@ -12,6 +12,7 @@
 //   * the NEXT window's input is fetched and published (lrelu -> fp16 operand) while the second convs of
 //     the current window still run, so the issuer never waits for global memory.
 // TMEM (512 columns): T_j = [128 j, 128 j + 128) for the two 128-row tiles of chain j, S = [384, 512).
+#include <cstdio>
 #include <cstdlib>
 #include <stdexcept>
 
@@ -22,7 +23,7 @@ namespace m3 {
 
 namespace {
 constexpr int wC = 64, wNT = 2, wR = wNT * 128, wCH = wC / 8, wKS = wC / 16;
-constexpr int wEpiWarps = 16, wIssuer = 16, wLoader = 17, wThreads = 32 * 18;
+constexpr int wEpiWarps = 8, wIssuer = 8, wIssuers = wNT, wLoader = wIssuer + wIssuers, wThreads = 32 * (wLoader + 1);
 constexpr int wSegTable = 1024;  // per-utterance row counts cached in shared memory (larger batches read global memory)
 constexpr uint32_t wTapBytes = wC * wC * 2;
 constexpr uint32_t wS0 = 384;
@@ -51,6 +52,23 @@ __host__ __device__ inline WGeo make_wgeo(const MrfParams& p, int nslot) {
   return g;
 }
 __device__ __forceinline__ float wlrelu(float v, float s) { return fmaxf(v, s * v); }
+// 256-bit global accesses: one full 32-byte sector per lane and instruction (the row-per-lane pattern of the
+// epilogue warps touches 32 different lines per instruction; L1 handles one line per cycle)
+__device__ __forceinline__ void ldg256(const float* p, float* v) {
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void stg256(float* p, const float* v) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};\n" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+               "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p)); }
+// chain order of a window: rotated by the window index, so that the SMs (which work on different windows at
+// any moment) do not all pull the same weight block from the same L2 slices at the same time; a function of
+// the window only, so results do not depend on the batch composition
+__device__ __forceinline__ int chain_at(int win, int pos) { return (win + pos) % 3; }
 }  // namespace
 
 template <int FMT>
@@ -86,7 +104,8 @@ __global__ void __launch_bounds__(wThreads, 1) mrf_ws_kernel(MrfParams p) {
   if (tid == 0) {
     for (int i = 0; i < WNBAR; ++i) {
       const bool many = i == WX_READY || (i >= WY_READY && i < WY_READY + 3) || i == WF_DONE;
-      tc::mbar_init(&bars[i], many ? wEpiWarps : 1);
+      const bool from_issuers = (i >= WC1_DONE && i < WC1_DONE + 3) || i == WC2_DONE || i >= WEMPTY;  // one commit per issuer
+      tc::mbar_init(&bars[i], many ? wEpiWarps : (from_issuers ? wIssuers : 1));
     }
     tc::mbar_fence_init();
   }
@@ -111,12 +130,22 @@ __global__ void __launch_bounds__(wThreads, 1) mrf_ws_kernel(MrfParams p) {
     // one elected thread: the tap sequence of every window is (conv1 of chains 0..2, conv2 of chains 0..2)
     if (tc::elect_one()) {
       uint32_t slot = 0, eparity = 1u;  // waiting on parity 1 of a fresh barrier passes at once (first use of a slot)
+      long long l_empty = 0, l_blocked = 0;
       for (int idx = first; idx < total; idx = next_item(idx)) {
+        const int win = idx % p.max_win;
         for (int d = 0; d < 2; ++d)
-          for (int j = 0; j < 3; ++j) {
+          for (int jj = 0; jj < 3; ++jj) {
+            const int j = chain_at(win, jj);
             const uint16_t* src = p.w16 + p.woff[j][d];
             for (int t = 0; t < p.k[j]; ++t) {
-              tc::mbar_wait(&bars[WEMPTY + slot], eparity);
+              if (p.prof && !tc::mbar_test(&bars[WEMPTY + slot], eparity)) {
+                const long long t0 = clock64();
+                tc::mbar_wait(&bars[WEMPTY + slot], eparity);
+                l_empty += clock64() - t0;
+                ++l_blocked;
+              } else {
+                tc::mbar_wait(&bars[WEMPTY + slot], eparity);
+              }
               tc::mbar_expect_tx(&bars[WFULL + slot], wTapBytes);
               tc::bulk_g2s(ring + size_t(slot) * wTapBytes, src + size_t(t) * wC * wC, wTapBytes, &bars[WFULL + slot]);
               if (++slot == uint32_t(nslot)) {
@@ -126,18 +155,40 @@ __global__ void __launch_bounds__(wThreads, 1) mrf_ws_kernel(MrfParams p) {
             }
           }
       }
+      if (p.prof) {
+        atomicAdd(reinterpret_cast<unsigned long long*>(p.prof + 14), (unsigned long long)l_empty);
+        atomicAdd(reinterpret_cast<unsigned long long*>(p.prof + 15), (unsigned long long)l_blocked);
+      }
     }
     __syncwarp();
-  } else if (warp == wIssuer) {
-    // =================================== MMA issuer ===============================================
-    // ONE thread runs the whole schedule (waits included): no per-tap warp reconvergence, no divisions, and
+  } else if (warp >= wIssuer && warp < wIssuer + wIssuers) {
+    // =================================== MMA issuers ==============================================
+    // One issuer per 128-row tile (independent accumulators): a single thread could not keep the tensor pipe
+    // busy (its per-tap instruction stream took ~640 cycles against 390 cycles of MMA time, measured with the
+    // M3B200_MRF_PROFILE counters).  In each issuer warp ONE thread runs the whole schedule (waits included): no per-tap warp reconvergence, no divisions, and
     // the descriptors of a conv differ only by small additive constants in their low word (the 14-bit start
     // address never overflows: shared memory is < 256 KB), so each MMA costs one add and the instruction.
     if (tc::elect_one()) {
       const uint32_t idesc = tc::make_idesc(128, wC, FMT);
       const uint64_t b_tmpl = tc::make_desc(tc::smem_u32(ring), uint32_t(wC) * 16u, 128u);
       const uint32_t b_hi = uint32_t(b_tmpl >> 32), b_lo0 = uint32_t(b_tmpl);
+      const int my_tile = warp - wIssuer;
       uint32_t slot = 0, fparity = 0u;
+      long long c_full = 0, c_x = 0, c_y = 0, c_f = 0;
+      const bool prof = p.prof != nullptr;
+      const long long c_start = clock64();
+      long long n_blocked = 0;
+      auto timed_wait = [&](uint64_t* bar, uint32_t parity, long long& acc) {
+        if (prof) {  // only waits that actually block are timed (a probe that succeeds costs nothing)
+          if (tc::mbar_test(bar, parity)) return;
+          const long long t0 = clock64();
+          tc::mbar_wait(bar, parity);
+          acc += clock64() - t0;
+          if (&acc == &c_full) ++n_blocked;
+        } else {
+          tc::mbar_wait(bar, parity);
+        }
+      };
       auto conv = [&](uint32_t abase, int rows_in, int halo, int k, int dil, uint32_t dcol, bool acc0) {
         const uint64_t a_tmpl = tc::make_desc(abase, uint32_t(rows_in) * 16u, 128u);
         const uint32_t a_hi = uint32_t(a_tmpl >> 32);
@@ -145,18 +196,15 @@ __global__ void __launch_bounds__(wThreads, 1) mrf_ws_kernel(MrfParams p) {
         const uint32_t kstep = uint32_t(2 * rows_in);
 #pragma unroll 1
         for (int t = 0; t < k; ++t, at += uint32_t(dil)) {
-          tc::mbar_wait(&bars[WFULL + slot], fparity);
+          timed_wait(&bars[WFULL + slot], fparity, c_full);
           tc::fence_after_sync();
           const uint32_t bt = b_lo0 + slot * (wTapBytes >> 4);
 #pragma unroll
           for (int ks = 0; ks < wKS; ++ks) {
             const uint64_t bd = (uint64_t(b_hi) << 32) | uint64_t(bt + uint32_t(ks * 2 * wC));
             const uint32_t acc = (ks > 0 || acc0 || t > 0) ? 1u : 0u;
-#pragma unroll
-            for (int m = 0; m < wNT; ++m) {
-              const uint64_t ad = (uint64_t(a_hi) << 32) | uint64_t(at + uint32_t(ks) * kstep + uint32_t(m * 128));
-              tc::mma_f16_ss(tmem + dcol + uint32_t(m * wC), ad, bd, idesc, acc);
-            }
+            const uint64_t ad = (uint64_t(a_hi) << 32) | uint64_t(at + uint32_t(ks) * kstep + uint32_t(my_tile * 128));
+            tc::mma_f16_ss(tmem + dcol + uint32_t(my_tile * wC), ad, bd, idesc, acc);
           }
           tc::mma_commit(&bars[WEMPTY + slot]);
           if (++slot == uint32_t(nslot)) {
@@ -168,32 +216,44 @@ __global__ void __launch_bounds__(wThreads, 1) mrf_ws_kernel(MrfParams p) {
       int it = 0;
       for (int idx = first; idx < total; idx = next_item(idx), ++it) {
         const uint32_t par = uint32_t(it) & 1u;
-        tc::mbar_wait(&bars[WX_READY], par);
+        const int win = idx % p.max_win;
+        timed_wait(&bars[WX_READY], par, c_x);
         tc::fence_after_sync();
-        for (int j = 0; j < 3; ++j) {
-          if (j == 2 && it > 0) {  // T_2 still holds the previous window's sum until its final epilogue has read it
-            tc::mbar_wait(&bars[WF_DONE], uint32_t(it - 1) & 1u);
+        for (int jj = 0; jj < 3; ++jj) {
+          const int j = chain_at(win, jj);
+          if (jj == 2 && it > 0) {  // this T tile still holds the previous window's sum until its final epilogue has read it
+            timed_wait(&bars[WF_DONE], uint32_t(it - 1) & 1u, c_f);
             tc::fence_after_sync();
           }
           conv(tc::smem_u32(bufX), g.rows_x, p.HX, p.k[j], p.dil[j][0], uint32_t(j) * 128u, false);
           tc::mma_commit(&bars[WC1_DONE + j]);
         }
-        for (int j = 0; j < 3; ++j) {
-          tc::mbar_wait(&bars[WY_READY + j], par);
+        for (int jj = 0; jj < 3; ++jj) {
+          const int j = chain_at(win, jj);
+          timed_wait(&bars[WY_READY + j], par, c_y);
           tc::fence_after_sync();
-          conv(tc::smem_u32(smem + g.off_y[j]), g.rows_y[j], g.hy[j], p.k[j], p.dil[j][1], wS0, j > 0);
+          conv(tc::smem_u32(smem + g.off_y[j]), g.rows_y[j], g.hy[j], p.k[j], p.dil[j][1], wS0, jj > 0);
         }
         tc::mma_commit(&bars[WC2_DONE]);
+      }
+      if (prof && my_tile == 0) {
+        atomicAdd(reinterpret_cast<unsigned long long*>(p.prof + 0), (unsigned long long)(clock64() - c_start));
+        atomicAdd(reinterpret_cast<unsigned long long*>(p.prof + 1), (unsigned long long)c_full);
+        atomicAdd(reinterpret_cast<unsigned long long*>(p.prof + 2), (unsigned long long)c_x);
+        atomicAdd(reinterpret_cast<unsigned long long*>(p.prof + 3), (unsigned long long)c_y);
+        atomicAdd(reinterpret_cast<unsigned long long*>(p.prof + 4), (unsigned long long)c_f);
+        atomicAdd(reinterpret_cast<unsigned long long*>(p.prof + 5), (unsigned long long)it);
+        atomicAdd(reinterpret_cast<unsigned long long*>(p.prof + 6), (unsigned long long)n_blocked);
       }
     }
     __syncwarp();
   } else {
     // =================================== epilogue warps ===========================================
-    // warp w: TMEM lane quarter q = w & 3 (hardware restriction), column group cg = w >> 2 (16 channels)
-    const int q = warp & 3, cg = warp >> 2;
+    // warp w: TMEM lane quarter q = w & 3 (hardware restriction), channel half hh = w >> 2 (32 channels)
+    const int q = warp & 3, hh = warp >> 2;
     const uint32_t lane_base = tmem + (uint32_t(q * 32) << 16);
-    const int col0 = cg * 16;
-    float xr[wNT][16];  // this thread's x (fp32 residual source): rows {m*128 + q*32 + lane}, 16 channels
+    const int col0 = hh * 32;
+    float xr[wNT][32];  // this thread's x (fp32 residual source): rows {m*128 + q*32 + lane}, 32 channels
 
     auto arrive = [&](int b) {
       tc::fence_async_smem();
@@ -201,8 +261,8 @@ __global__ void __launch_bounds__(wThreads, 1) mrf_ws_kernel(MrfParams p) {
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&bars[b]);
     };
-    // 16 channels of one row -> two 16-byte operand chunks
-    auto store_ops = [&](uint8_t* buf, int pitch, int row, const float* v, bool inside) {
+    // 16 channels (half h of this thread's 32) of one row -> two 16-byte operand chunks
+    auto store_ops = [&](uint8_t* buf, int pitch, int row, int h, const float* v, bool inside) {
 #pragma unroll
       for (int c8 = 0; c8 < 2; ++c8) {
         uint4 pk = make_uint4(0u, 0u, 0u, 0u);
@@ -212,7 +272,7 @@ __global__ void __launch_bounds__(wThreads, 1) mrf_ws_kernel(MrfParams p) {
           pk.z = E::pack2(wlrelu(v[8 * c8 + 4], 0.1f), wlrelu(v[8 * c8 + 5], 0.1f));
           pk.w = E::pack2(wlrelu(v[8 * c8 + 6], 0.1f), wlrelu(v[8 * c8 + 7], 0.1f));
         }
-        *reinterpret_cast<uint4*>(buf + (size_t(cg * 2 + c8) * pitch + row) * 16) = pk;
+        *reinterpret_cast<uint4*>(buf + (size_t(hh * 4 + h * 2 + c8) * pitch + row) * 16) = pk;
       }
     };
     // fetch the window's x: own rows into registers (fp32 residual) and, as lrelu -> 16-bit, into bufX
@@ -224,51 +284,62 @@ __global__ void __launch_bounds__(wThreads, 1) mrf_ws_kernel(MrfParams p) {
       const int w0 = win * p.stride - p.H;
 #pragma unroll
       for (int m = 0; m < wNT; ++m) {
-        const int r = m * 128 + q * 32 + lane;
-        const int gi = w0 + r;
-        const bool inside = gi >= 0 && gi < L;
-        const float4* src = reinterpret_cast<const float4*>(p.x + (base + gi) * wC + col0);
+        const int gi = w0 + m * 128 + q * 32 + lane;
+        const float* src = p.x + (base + gi) * wC + col0;
+        if (gi >= 0 && gi < L) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (inside) t = __ldg(src + e);
-          xr[m][4 * e] = t.x;
-          xr[m][4 * e + 1] = t.y;
-          xr[m][4 * e + 2] = t.z;
-          xr[m][4 * e + 3] = t.w;
+          for (int e = 0; e < 4; ++e) ldg256(src + 8 * e, &xr[m][8 * e]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) xr[m][e] = 0.f;
         }
       }
-      float4 ha = make_float4(0.f, 0.f, 0.f, 0.f), hb = ha;
-      const int hi = tid;  // halo item: (row rr of the 2*HX halo rows, chunk c8)
-      const bool has_halo = hi < 2 * p.HX * wCH;
+      float hv[8];
+      const bool has_halo = tid < 2 * p.HX * wCH;  // halo item: (row rr of the 2*HX halo rows, chunk c8)
       int hrow = 0, hc8 = 0;
+      bool hin = false;
       if (has_halo) {
-        const int rr = hi / wCH;
-        hc8 = hi - rr * wCH;
+        const int rr = tid / wCH;
+        hc8 = tid - rr * wCH;
         hrow = rr < p.HX ? rr : wR + rr;  // bufX rows [0, HX) and [R + HX, R + 2 HX)
         const int gi = w0 - p.HX + hrow;
-        if (gi >= 0 && gi < L) {
-          const float4* src = reinterpret_cast<const float4*>(p.x + (base + gi) * wC + hc8 * 8);
-          ha = __ldg(src);
-          hb = __ldg(src + 1);
-        }
+        hin = gi >= 0 && gi < L;
+        if (hin) ldg256(p.x + (base + gi) * wC + hc8 * 8, hv);
       }
 #pragma unroll
       for (int m = 0; m < wNT; ++m) {
         const int r = m * 128 + q * 32 + lane;
         const int gi = w0 + r;
-        store_ops(bufX, g.rows_x, r + p.HX, xr[m], gi >= 0 && gi < L);
+        store_ops(bufX, g.rows_x, r + p.HX, 0, xr[m], gi >= 0 && gi < L);
+        store_ops(bufX, g.rows_x, r + p.HX, 1, xr[m] + 16, gi >= 0 && gi < L);
       }
       if (has_halo) {
-        uint4 pk;
-        pk.x = E::pack2(wlrelu(ha.x, 0.1f), wlrelu(ha.y, 0.1f));
-        pk.y = E::pack2(wlrelu(ha.z, 0.1f), wlrelu(ha.w, 0.1f));
-        pk.z = E::pack2(wlrelu(hb.x, 0.1f), wlrelu(hb.y, 0.1f));
-        pk.w = E::pack2(wlrelu(hb.z, 0.1f), wlrelu(hb.w, 0.1f));
+        uint4 pk = make_uint4(0u, 0u, 0u, 0u);
+        if (hin) {
+          pk.x = E::pack2(wlrelu(hv[0], 0.1f), wlrelu(hv[1], 0.1f));
+          pk.y = E::pack2(wlrelu(hv[2], 0.1f), wlrelu(hv[3], 0.1f));
+          pk.z = E::pack2(wlrelu(hv[4], 0.1f), wlrelu(hv[5], 0.1f));
+          pk.w = E::pack2(wlrelu(hv[6], 0.1f), wlrelu(hv[7], 0.1f));
+        }
         *reinterpret_cast<uint4*>(bufX + (size_t(hc8) * g.rows_x + hrow) * 16) = pk;
       }
     };
+    // pull a window's x rows into L2 one window ahead of their use (no registers involved)
+    auto prefetch_x = [&](int idx) {
+      const int seg = idx / p.max_win, win = idx - seg * p.max_win;
+      const int L = seg_rows(seg);
+      const long long base = (long long)p.seg_off[seg] * p.scale;
+      const int w0 = win * p.stride - p.H;
+#pragma unroll
+      for (int m = 0; m < wNT; ++m) {
+        const int gi = w0 + m * 128 + q * 32 + lane;
+        if (gi >= 0 && gi < L) prefetch_l2(p.x + (base + gi) * wC + col0);
+      }
+    };
 
+    const bool prof = p.prof != nullptr && tid == 0;
+    long long e_c1w = 0, e_c1 = 0, e_lx = 0, e_c2w = 0, e_fin = 0, e_t = 0;
+    const long long e_start = clock64();
     if (first < total) {
       load_x(first);
       arrive(WX_READY);
@@ -278,44 +349,62 @@ __global__ void __launch_bounds__(wThreads, 1) mrf_ws_kernel(MrfParams p) {
       const int nxt = next_item(idx);
       const uint32_t par = uint32_t(it) & 1u;
       const int seg = idx / p.max_win, win = idx - seg * p.max_win;
-      const int L = seg_rows(seg);
-      const long long base = (long long)p.seg_off[seg] * p.scale;
       const int w0 = win * p.stride - p.H;
+      if (nxt < total) {
+        const int nn = next_item(nxt);
+        if (nn < total) prefetch_x(nn);
+      }
+      // TMEM tile that keeps sum_j x1_j until the final epilogue: the chain the NEXT window runs last, so the
+      // issuer (which waits for WF_DONE before that chain's first conv) is never held up by it
+      const int park = nxt < total ? chain_at(nxt % p.max_win, 2) : chain_at(win, 2);
 
       // ---- first conv of each chain: x1_j = x + b + conv(lrelu x); second conv's operand = lrelu(x1_j).
-      // The running sum of the x1_j lives in TMEM: in T_0 after chains 0 and 1, in T_2 after chain 2
-      // (T_0 is overwritten by the next window's first conv before the final epilogue runs, T_2 is not:
-      // the issuer waits for WF_DONE before it touches T_2 again).
+      // The running sum of the x1_j is parked in TMEM tiles that are idle at that point.
 #pragma unroll 1
-      for (int j = 0; j < 3; ++j) {
+      for (int jj = 0; jj < 3; ++jj) {
+        const int j = chain_at(win, jj), j0 = chain_at(win, 0);
+        if (prof) e_t = clock64();
         tc::mbar_wait(&bars[WC1_DONE + j], par);
+        if (prof) {
+          const long long t1 = clock64();
+          e_c1w += t1 - e_t;
+          e_t = t1;
+        }
         tc::fence_after_sync();
         uint8_t* by = smem + g.off_y[j];
         const int pitch = g.rows_y[j], hy = g.hy[j];
+        const int L = seg_rows(seg);
+        const uint32_t dst_tile = uint32_t(jj == 2 ? park : j0) * 128u;
 #pragma unroll
         for (int m = 0; m < wNT; ++m) {
-          float v[16], acc[16];
-          tc::tmem_ld16(lane_base + uint32_t(j * 128 + m * wC + col0), v);
-          if (j > 0) tc::tmem_ld16(lane_base + uint32_t(m * wC + col0), acc);
-          tc::tmem_ld_wait();
           const int r = m * 128 + q * 32 + lane;
           const int gi = w0 + r;
+          const bool inside = gi >= 0 && gi < L;
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const float4 bb = *reinterpret_cast<const float4*>(&sbias[j][col0 + 4 * c]);
-            v[4 * c] += xr[m][4 * c] + bb.x;
-            v[4 * c + 1] += xr[m][4 * c + 1] + bb.y;
-            v[4 * c + 2] += xr[m][4 * c + 2] + bb.z;
-            v[4 * c + 3] += xr[m][4 * c + 3] + bb.w;
+          for (int h = 0; h < 2; ++h) {
+            float v[16], acc[16];
+            tc::tmem_ld16(lane_base + uint32_t(j * 128 + m * wC + col0 + 16 * h), v);
+            if (jj > 0) tc::tmem_ld16(lane_base + uint32_t(j0 * 128 + m * wC + col0 + 16 * h), acc);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const float4 bb = *reinterpret_cast<const float4*>(&sbias[j][col0 + 16 * h + 4 * c]);
+              v[4 * c] += xr[m][16 * h + 4 * c] + bb.x;
+              v[4 * c + 1] += xr[m][16 * h + 4 * c + 1] + bb.y;
+              v[4 * c + 2] += xr[m][16 * h + 4 * c + 2] + bb.z;
+              v[4 * c + 3] += xr[m][16 * h + 4 * c + 3] + bb.w;
+            }
+#pragma unroll
+            for (int c = 0; c < 16; ++c) acc[c] = jj > 0 ? acc[c] + v[c] : v[c];
+            tc::tmem_st16(lane_base + dst_tile + uint32_t(m * wC + col0 + 16 * h), acc);
+            store_ops(by, pitch, r + hy, h, v, inside);
           }
-#pragma unroll
-          for (int c = 0; c < 16; ++c) acc[c] = j > 0 ? acc[c] + v[c] : v[c];
-          tc::tmem_st16(lane_base + uint32_t((j == 2 ? 256 : 0) + m * wC + col0), acc);
-          store_ops(by, pitch, r + hy, v, gi >= 0 && gi < L);
         }
         tc::tmem_st_wait();
         arrive(WY_READY + j);
+        if (prof) e_c1 += clock64() - e_t;
       }
+      if (prof) e_t = clock64();
 
       // ---- next window's input while this window's second convs run ----
       if (nxt < total) {
@@ -324,38 +413,63 @@ __global__ void __launch_bounds__(wThreads, 1) mrf_ws_kernel(MrfParams p) {
       }
 
       // ---- out = (sum_j x1_j + S + late bias) / nk ----
+      if (prof) {
+        const long long t1 = clock64();
+        e_lx += t1 - e_t;
+        e_t = t1;
+      }
       tc::mbar_wait(&bars[WC2_DONE], par);
+      if (prof) {
+        const long long t1 = clock64();
+        e_c2w += t1 - e_t;
+        e_t = t1;
+      }
       tc::fence_after_sync();
       {
+        const int L = seg_rows(seg);
+        const long long base = (long long)p.seg_off[seg] * p.scale;
 #pragma unroll
         for (int m = 0; m < wNT; ++m) {
-          float v[16], acc[16];
-          tc::tmem_ld16(lane_base + wS0 + uint32_t(m * wC + col0), v);
-          tc::tmem_ld16(lane_base + 256u + uint32_t(m * wC + col0), acc);
-          tc::tmem_ld_wait();
-          if (m == wNT - 1) {  // T_2 and S are consumed
-            tc::fence_before_sync();
-            __syncwarp();
-            if (lane == 0) tc::mbar_arrive(&bars[WF_DONE]);
-          }
           const int r = m * 128 + q * 32 + lane;
           const int gi = w0 + r;
-          if (r >= p.H && r < wR - p.H && gi < L) {
-            float4* dst = reinterpret_cast<float4*>(p.out + (base + gi) * wC + col0);
+          const bool store = r >= p.H && r < wR - p.H && gi < L;
+          float* dst = p.out + (base + gi) * wC + col0;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              const float4 bb = *reinterpret_cast<const float4*>(&sbias[3][col0 + 4 * c]);
-              float4 o;
-              o.x = (v[4 * c] + acc[4 * c] + bb.x) * p.inv_nk;
-              o.y = (v[4 * c + 1] + acc[4 * c + 1] + bb.y) * p.inv_nk;
-              o.z = (v[4 * c + 2] + acc[4 * c + 2] + bb.z) * p.inv_nk;
-              o.w = (v[4 * c + 3] + acc[4 * c + 3] + bb.w) * p.inv_nk;
-              dst[c] = o;
+          for (int h = 0; h < 2; ++h) {
+            float v[16], acc[16];
+            tc::tmem_ld16(lane_base + wS0 + uint32_t(m * wC + col0 + 16 * h), v);
+            tc::tmem_ld16(lane_base + uint32_t(park * 128 + m * wC + col0 + 16 * h), acc);
+            tc::tmem_ld_wait();
+            if (m == wNT - 1 && h == 1) {  // the parked sum and S are consumed
+              tc::fence_before_sync();
+              __syncwarp();
+              if (lane == 0) tc::mbar_arrive(&bars[WF_DONE]);
+            }
+            if (store) {
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                const float4 bb = *reinterpret_cast<const float4*>(&sbias[3][col0 + 16 * h + 4 * c]);
+                v[4 * c] = (v[4 * c] + acc[4 * c] + bb.x) * p.inv_nk;
+                v[4 * c + 1] = (v[4 * c + 1] + acc[4 * c + 1] + bb.y) * p.inv_nk;
+                v[4 * c + 2] = (v[4 * c + 2] + acc[4 * c + 2] + bb.z) * p.inv_nk;
+                v[4 * c + 3] = (v[4 * c + 3] + acc[4 * c + 3] + bb.w) * p.inv_nk;
+              }
+              stg256(dst + 16 * h, v);
+              stg256(dst + 16 * h + 8, v + 8);
             }
           }
         }
       }
+      if (prof) e_fin += clock64() - e_t;
       idx = nxt;
+    }
+    if (prof) {
+      atomicAdd(reinterpret_cast<unsigned long long*>(p.prof + 8), (unsigned long long)(clock64() - e_start));
+      atomicAdd(reinterpret_cast<unsigned long long*>(p.prof + 9), (unsigned long long)e_c1w);
+      atomicAdd(reinterpret_cast<unsigned long long*>(p.prof + 10), (unsigned long long)e_c1);
+      atomicAdd(reinterpret_cast<unsigned long long*>(p.prof + 11), (unsigned long long)e_lx);
+      atomicAdd(reinterpret_cast<unsigned long long*>(p.prof + 12), (unsigned long long)e_c2w);
+      atomicAdd(reinterpret_cast<unsigned long long*>(p.prof + 13), (unsigned long long)e_fin);
     }
   }
   tc::fence_before_sync();
@@ -405,9 +519,28 @@ void launch_mrf_ws(const MrfParams& p_in, int fmt, int n_seg, int max_len, cudaS
   ensure_max_dynamic_smem(kern);
   const long long items = (long long)n_seg * p.max_win;
   const int grid = int(items < n_sm ? items : n_sm);
+  static const bool want_prof = getenv("M3B200_MRF_PROFILE") != nullptr;
+  static long long* d_prof = nullptr;
+  if (want_prof) {
+    if (!d_prof) cudaMalloc(&d_prof, 16 * sizeof(long long));
+    cudaMemsetAsync(d_prof, 0, 16 * sizeof(long long), st);
+    p.prof = d_prof;
+  }
   if (fmt) mrf_ws_kernel<1><<<grid, wThreads, smem, st>>>(p);
   else mrf_ws_kernel<0><<<grid, wThreads, smem, st>>>(p);
   post_launch("mrf_ws_kernel", st);
+  if (want_prof) {  // debug only: synchronous read-back of the per-role cycle counters (summed over CTAs)
+    long long h[16];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, d_prof, sizeof h, cudaMemcpyDeviceToHost);
+    const double w = h[5] > 0 ? double(h[5]) : 1.0;
+    fprintf(stderr,
+            "[mrf_ws profile] windows %lld grid %d | issuer cycles/window: total %.0f wait_full %.0f wait_x %.0f wait_y %.0f wait_f %.0f | "
+            "epilogue warp0: total %.0f wait_c1 %.0f c1_body %.0f load_x %.0f wait_c2 %.0f final %.0f | blocked FULL waits/window %.1f, "
+            "loader: EMPTY-blocked cycles/window %.0f (%.1f waits)\n",
+            h[5], grid, h[0] / w, h[1] / w, h[2] / w, h[3] / w, h[4] / w, h[8] / w, h[9] / w, h[10] / w, h[11] / w, h[12] / w, h[13] / w,
+            h[6] / w, h[14] / w, h[15] / w);
+  }
 }
 
 }  // namespace m3
