@@ -115,16 +115,17 @@ struct Builder {
   }
 
   // fp16 hi/lo split packing of W[tap][k][n] for rowgemm_tc_kernel:
-  // [chunk][K block][tap][hi|lo][4][64][8]
+  // [chunk][K block][tap][hi|lo][4][nc][8]
   void rows_pack(RowTcW& t, const std::vector<float>& W, int taps, int K, int N) {
     t.ok = false;
     if (!rowgemm_tc_supported(K, taps)) return;
-    const int KB = 32, NCc = 64;
+    const int KB = 32, NCc = rowgemm_tc_nc(N, taps);
+    t.nc = NCc;
     const int chunks = (N + NCc - 1) / NCc, nkb = K / KB;
     while (h16.size() % 64) h16.push_back(0);
     t.woff = h16.size();
     const size_t o = h16.size();
-    h16.resize(o + rowgemm_tc_weight_elems(K, N, taps), 0);
+    h16.resize(o + rowgemm_tc_weight_elems(K, N, taps, NCc), 0);
     for (int c = 0; c < chunks; ++c)
       for (int kb = 0; kb < nkb; ++kb)
         for (int tap = 0; tap < taps; ++tap)
@@ -833,6 +834,7 @@ struct Run {
       q.w = dv.slab16 + l.rtc.woff;
       q.N = l.cout;
       q.taps = l.taps;
+      q.nc = l.rtc.nc;
       q.pad_left = (l.taps - 1) / 2;
       q.bias = l.b;
       q.ubias = ub;

@@ -35,6 +35,7 @@ struct TcConvW {  // 16-bit tensor-core packing [chunk][tap][K/8][NC][8] (kernel
 struct RowTcW {  // fp16 hi/lo split packing for rowgemm_tc_kernel (kernels_tc_rows.cu)
   bool ok = false;
   unsigned long long woff = 0;
+  int nc = 64;  // output columns per CTA the block layout was built for (rowgemm_tc_nc)
 };
 
 struct Lin {  // a Conv1d packed as [taps][Cin][ldw] (+ bias[ldw])

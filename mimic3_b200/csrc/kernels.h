@@ -117,12 +117,13 @@ bool conv_tc_supported(int K, int NC, int taps, int dil);
 void launch_conv_tc(const TcConvParams& p, int fmt, int n_seg, int max_seg_len, cudaStream_t st);
 
 // Token-level conv-as-GEMM on tensor cores with fp16 hi/lo split operands (kernels_tc_rows.cu).
-// Weights: [chunk(64 cols)][K block(32)][tap][hi|lo][4][64][8], 16-bit.
+// Weights: [chunk(nc cols)][K block(32)][tap][hi|lo][4][nc][8], 16-bit; nc = rowgemm_tc_nc(N, taps).
 struct RowGemmTcParams {
   const float* in = nullptr;
   int in_stride = 0, K = 0;
   const uint16_t* w = nullptr;
   int N = 0, taps = 1, pad_left = 0;
+  int nc = 64;                    // output columns per CTA the weights were packed for
   const float* bias = nullptr;
   const float* ubias = nullptr;
   int ub_stride = 0;
@@ -134,7 +135,8 @@ struct RowGemmTcParams {
   int vrows = 0;
 };
 bool rowgemm_tc_supported(int K, int taps);
-size_t rowgemm_tc_weight_elems(int K, int N, int taps);
+int rowgemm_tc_nc(int N, int taps);
+size_t rowgemm_tc_weight_elems(int K, int N, int taps, int nc);
 void launch_rowgemm_tc(const RowGemmTcParams& p, cudaStream_t st);
 void launch_fill_vmap(int* vmap, const int* seg_off, const int* seg_len, int n_seg, int max_len, cudaStream_t st);
 
@@ -239,6 +241,11 @@ void launch_gather_rows(const int64_t* idx, const float* table, float* out, int 
 void launch_attention(const float* qkv, const float* emb_rel_k, const float* emb_rel_v, float* out, int H,
                       int n_heads, int window, const int* seg_off, const int* seg_len, int n_seg, int max_len,
                       cudaStream_t st);
+// short-sequence variant (kernels_attn.cu): whole (utterance, head) in shared memory; returns false when the
+// shape does not fit and the generic kernel has to run (M3B200_ATTN_V1=1 forces that)
+bool launch_attention_short(const float* qkv, const float* emb_rel_k, const float* emb_rel_v, float* out, int H,
+                            int n_heads, int window, const int* seg_off, const int* seg_len, int n_seg, int max_len,
+                            cudaStream_t st);
 // u[t][c] = z[t][zc]*w[c] + b[c] + h[t][c]
 void launch_convflow_pre(const float* z, int zc, const float* w, const float* b, const float* h, float* out,
                          int rows, int C, cudaStream_t st);

@@ -719,6 +719,8 @@ void launch_attention(const float* qkv, const float* emb_rel_k, const float* emb
                       int n_heads, int window, const int* seg_off, const int* seg_len, int n_seg, int max_len,
                       cudaStream_t st) {
   if (max_len <= 0) return;
+  // short sequences: whole (utterance, head) resident in shared memory (kernels_attn.cu)
+  if (launch_attention_short(qkv, emb_rel_k, emb_rel_v, out, H, n_heads, window, seg_off, seg_len, n_seg, max_len, st)) return;
   const int dk = H / n_heads;
   const int nrel = 2 * window + 1;
   const size_t smem = sizeof(float) * (size_t(2) * dk * (AQ + 4) + AKT * dk + AQ * (AKT + 1) + AQ * nrel +

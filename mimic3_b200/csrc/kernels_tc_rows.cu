@@ -7,10 +7,12 @@
 //
 // Rows are the packed tokens of all utterances with ONE virtual zero row after each utterance, so a
 // k=3 tap is a descriptor shift even across utterance boundaries (vmap[v] = physical row or -1).
-// CTA = 128 virtual rows x 64 output columns; K streamed in blocks of 32 through a 2-stage ring:
+// CTA = 128 virtual rows x NC output columns (64, or 128 for the 1x1 layers with M3B200_ROWGEMM_NC=128: half as
+// many CTAs re-stage the same A rows); K streamed in blocks of 32 through a 2- or 3-stage ring:
 //   warps 0-3  convert the fp32 A block to hi/lo fp16 (interleaved layout) -- and run the epilogue;
 //   warp 4     one thread: bulk-copies the pre-split weight block of all taps (one copy per stage);
 //   warp 5     one thread: issues the MMAs, frees stages with tcgen05.commit.
+#include <cstdlib>
 #include <stdexcept>
 
 #include "kernels.h"
@@ -19,8 +21,6 @@
 namespace m3 {
 
 constexpr int RG_KB = 32;       // K block
-constexpr int RG_NC = 64;       // output columns per CTA
-constexpr int RG_STAGES = 2;
 constexpr int RG_THREADS = 192;
 
 __global__ void fill_vmap_kernel(int* vmap, const int* seg_off, const int* seg_len, int n_seg) {
@@ -38,7 +38,8 @@ void launch_fill_vmap(int* vmap, const int* seg_off, const int* seg_len, int n_s
   post_launch("fill_vmap_kernel", st);
 }
 
-__global__ void __launch_bounds__(RG_THREADS, 2) rowgemm_tc_kernel(RowGemmTcParams p) {
+template <int RG_NC, int RG_STAGES>
+__global__ void __launch_bounds__(RG_THREADS, 4) rowgemm_tc_kernel(RowGemmTcParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(8) uint64_t a_full[RG_STAGES], w_full[RG_STAGES], empty_bar[RG_STAGES], acc_full;
@@ -54,7 +55,7 @@ __global__ void __launch_bounds__(RG_THREADS, 2) rowgemm_tc_kernel(RowGemmTcPara
   const int nkb = p.K / RG_KB;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-  if (warp == 0) tc::tmem_alloc<128>(&tmem_slot);
+  if (warp == 0) tc::tmem_alloc<2 * RG_NC>(&tmem_slot);
   if (tid == 32) {
     for (int s = 0; s < RG_STAGES; ++s) {
       tc::mbar_init(&a_full[s], 4);
@@ -140,16 +141,25 @@ __global__ void __launch_bounds__(RG_THREADS, 2) rowgemm_tc_kernel(RowGemmTcPara
       tc::tmem_ld_wait();
       if (phys < 0) continue;
       const int n0 = chunk * RG_NC + c0;
+      if (n0 >= p.N) continue;
       float* dst = p.out + (long long)phys * p.out_stride + n0;
+      float val[16];
 #pragma unroll
       for (int e = 0; e < 16; ++e) {
-        const int n = n0 + e;
-        if (n >= p.N) break;
-        float val = m[e] + c[e] * (1.0f / 2048.0f);
-        if (p.bias) val += p.bias[n];
-        if (p.ubias) val += p.ubias[(long long)seg * p.ub_stride + n];
-        if (p.act == 1) val = fmaxf(val, 0.f);
-        dst[e] = val;
+        const int n = n0 + e < p.N ? n0 + e : p.N - 1;
+        float v = m[e] + c[e] * (1.0f / 2048.0f);
+        if (p.bias) v += p.bias[n];
+        if (p.ubias) v += p.ubias[(long long)seg * p.ub_stride + n];
+        if (p.act == 1) v = fmaxf(v, 0.f);
+        val[e] = v;
+      }
+      if (n0 + 16 <= p.N && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {  // 4 x 128-bit stores per row
+#pragma unroll
+        for (int e = 0; e < 16; e += 4) *reinterpret_cast<float4*>(dst + e) = make_float4(val[e], val[e + 1], val[e + 2], val[e + 3]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 16; ++e)
+          if (n0 + e < p.N) dst[e] = val[e];
       }
     }
   } else if (warp == 4) {
@@ -199,24 +209,50 @@ __global__ void __launch_bounds__(RG_THREADS, 2) rowgemm_tc_kernel(RowGemmTcPara
   }
   tc::fence_before_sync();
   __syncthreads();
-  if (warp == 0) tc::tmem_dealloc<128>(tmem);
+  if (warp == 0) tc::tmem_dealloc<2 * RG_NC>(tmem);
 }
 
 bool rowgemm_tc_supported(int K, int taps) { return K % RG_KB == 0 && K >= RG_KB && (taps == 1 || taps == 3); }
 
-size_t rowgemm_tc_weight_elems(int K, int N, int taps) {
-  const int chunks = (N + RG_NC - 1) / RG_NC;
-  return size_t(chunks) * (K / RG_KB) * taps * 2 * RG_KB * RG_NC;
+// Output columns per CTA for a layer (fixed at voice-load time: the weight packing depends on it).
+int rowgemm_tc_nc(int N, int taps) {
+  static const int want = [] {
+    const char* e = getenv("M3B200_ROWGEMM_NC");
+    return e && atoi(e) == 128 ? 128 : 64;
+  }();
+  return (want == 128 && taps == 1 && N > 64) ? 128 : 64;
+}
+
+size_t rowgemm_tc_weight_elems(int K, int N, int taps, int nc) {
+  const int chunks = (N + nc - 1) / nc;
+  return size_t(chunks) * (K / RG_KB) * taps * 2 * RG_KB * nc;
+}
+
+template <int NC, int ST>
+static void launch_rowgemm_inst(const RowGemmTcParams& p, size_t stage_bytes, cudaStream_t st) {
+  ensure_max_dynamic_smem(reinterpret_cast<const void*>(rowgemm_tc_kernel<NC, ST>));
+  dim3 grid((p.vrows + 127) / 128, (p.N + NC - 1) / NC);
+  rowgemm_tc_kernel<NC, ST><<<grid, RG_THREADS, ST * stage_bytes, st>>>(p);
 }
 
 void launch_rowgemm_tc(const RowGemmTcParams& p, cudaStream_t st) {
   if (p.vrows <= 0) return;
+  if (p.nc != 64 && p.nc != 128) throw std::runtime_error("rowgemm_tc: unsupported column chunk");
   const int RA = (128 + p.taps - 1) | 1;
   const size_t a_pad = (size_t(2) * (RG_KB / 8) * RA * 16 + 127) & ~size_t(127);
-  const size_t smem = RG_STAGES * (a_pad + size_t(p.taps) * 2 * RG_KB * RG_NC * 2);
-  ensure_max_dynamic_smem(reinterpret_cast<const void*>(rowgemm_tc_kernel));
-  dim3 grid((p.vrows + 127) / 128, (p.N + RG_NC - 1) / RG_NC);
-  rowgemm_tc_kernel<<<grid, RG_THREADS, smem, st>>>(p);
+  const size_t stage = a_pad + size_t(p.taps) * 2 * RG_KB * p.nc * 2;
+  static const int want_stages = [] {
+    const char* e = getenv("M3B200_ROWGEMM_STAGES");
+    return e ? atoi(e) : 2;
+  }();
+  const bool deep = want_stages >= 3 && 3 * stage <= 100 * 1024;  // a third stage only while two CTAs still share an SM
+  if (p.nc == 64) {
+    if (deep) launch_rowgemm_inst<64, 3>(p, stage, st);
+    else launch_rowgemm_inst<64, 2>(p, stage, st);
+  } else {
+    if (deep) launch_rowgemm_inst<128, 3>(p, stage, st);
+    else launch_rowgemm_inst<128, 2>(p, stage, st);
+  }
   post_launch("rowgemm_tc_kernel", st);
 }
 
