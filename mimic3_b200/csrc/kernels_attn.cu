@@ -283,8 +283,8 @@ int attn_env(const char* name, int dflt) {
 bool launch_attention_short(const float* qkv, const float* emb_rel_k, const float* emb_rel_v, float* out, int H,
                             int n_heads, int window, const int* seg_off, const int* seg_len, int n_seg, int max_len,
                             cudaStream_t st) {
-  static const int forced_v1 = attn_env("M3B200_ATTN_V1", 0);
-  static const int forced_nb = attn_env("M3B200_ATTN_NB", 0);
+  const int forced_v1 = attn_env("M3B200_ATTN_V1", 0);  // read per launch: tests and A/B runs toggle it
+  const int forced_nb = attn_env("M3B200_ATTN_NB", 0);
   if (forced_v1 || max_len <= 0 || H % n_heads) return false;
   const int dk = H / n_heads, nrel = 2 * window + 1;
   if (dk % 4 || dk > 96 || dk < 4 || H % 4 || nrel > 28) return false;

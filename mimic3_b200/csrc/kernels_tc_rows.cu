@@ -216,10 +216,8 @@ bool rowgemm_tc_supported(int K, int taps) { return K % RG_KB == 0 && K >= RG_KB
 
 // Output columns per CTA for a layer (fixed at voice-load time: the weight packing depends on it).
 int rowgemm_tc_nc(int N, int taps) {
-  static const int want = [] {
-    const char* e = getenv("M3B200_ROWGEMM_NC");
-    return e && atoi(e) == 128 ? 128 : 64;
-  }();
+  const char* e = getenv("M3B200_ROWGEMM_NC");  // read when a voice is packed
+  const int want = e && atoi(e) == 128 ? 128 : 64;
   return (want == 128 && taps == 1 && N > 64) ? 128 : 64;
 }
 
@@ -241,10 +239,8 @@ void launch_rowgemm_tc(const RowGemmTcParams& p, cudaStream_t st) {
   const int RA = (128 + p.taps - 1) | 1;
   const size_t a_pad = (size_t(2) * (RG_KB / 8) * RA * 16 + 127) & ~size_t(127);
   const size_t stage = a_pad + size_t(p.taps) * 2 * RG_KB * p.nc * 2;
-  static const int want_stages = [] {
-    const char* e = getenv("M3B200_ROWGEMM_STAGES");
-    return e ? atoi(e) : 2;
-  }();
+  const char* es = getenv("M3B200_ROWGEMM_STAGES");
+  const int want_stages = es ? atoi(es) : 2;
   const bool deep = want_stages >= 3 && 3 * stage <= 100 * 1024;  // a third stage only while two CTAs still share an SM
   if (p.nc == 64) {
     if (deep) launch_rowgemm_inst<64, 3>(p, stage, st);

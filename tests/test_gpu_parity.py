@@ -353,3 +353,61 @@ def test_persistent_last_stage_matches_per_window_kernel_and_oracle(voices, buil
         print(f"utt {b} ({lens[b]} ids): RMS vs oracle {rms:.3e}")
         assert rms <= RMS_TOL
     sess.close()
+
+
+def test_short_attention_matches_generic_kernel(voices, built_library, monkeypatch):
+    """attention_short_kernel (whole utterance/head in shared memory, kernels_attn.cu) against the generic
+    flash-style kernel on ragged batches: one query block per utterance (max 128 ids), several query blocks
+    (max 200 ids), and the tiny voice (dk = 16).  Same encoder output to fp32 noise, identical durations."""
+    from mimic3_b200.engine import B200Session
+    rng = np.random.default_rng(91)
+    cases = [("low_ms", [1, 2, 5, 9, 31, 64, 80, 100, 128, 77]), ("low_ms", [200, 3, 150, 96]),
+             ("tiny_ms", [40, 1, 17, 33, 8])]
+    for voice, lens_list in cases:
+        sess = B200Session(str(voices(voice)))
+        ids, lens = _batch(rng, sess.info.num_symbols, lens_list)
+        sid = rng.integers(0, sess.info.n_speakers, size=len(lens_list))
+        names = ("x", "logw", "durations")
+        new = sess.infer(ids, lens, (0.0, 1.0, 0.0), sid, debug_tensors=names)
+        monkeypatch.setenv("M3B200_ATTN_V1", "1")
+        old = sess.infer(ids, lens, (0.0, 1.0, 0.0), sid, debug_tensors=names)
+        monkeypatch.delenv("M3B200_ATTN_V1")
+        dx = float(np.abs(new.tensors["x"] - old.tensors["x"]).max())
+        dl = float(np.abs(new.tensors["logw"] - old.tensors["logw"]).max())
+        print(f"{voice} {lens_list}: max|dx| {dx:.2e}  max|dlogw| {dl:.2e}  launches {new.launches} vs {old.launches}")
+        assert dx < 5e-5 and dl < 5e-5
+        np.testing.assert_array_equal(new.tensors["durations"], old.tensors["durations"])
+        np.testing.assert_array_equal(new.frames, old.frames)
+        for nb in ("1", "3"):   # forced query-block counts exercise the multi-block path on short rows too
+            monkeypatch.setenv("M3B200_ATTN_NB", nb)
+            alt = sess.infer(ids, lens, (0.0, 1.0, 0.0), sid, debug_tensors=names)
+            monkeypatch.delenv("M3B200_ATTN_NB")
+            assert float(np.abs(alt.tensors["x"] - old.tensors["x"]).max()) < 5e-5
+        sess.close()
+
+
+def test_rowgemm_variants_keep_text_side_results(voices, built_library, monkeypatch):
+    """128-column CTAs for the 1x1 layers and the 3-stage ring of rowgemm_tc_kernel are pure re-tilings:
+    same products in the same order per output, so the text side must not move at all."""
+    from mimic3_b200.engine import B200Session
+    rng = np.random.Generator(np.random.PCG64(5))
+    ids = rng.integers(4, 50, size=(24, 80)).astype(np.int64)
+    lens = np.full(24, 80, dtype=np.int64)
+    lens[3], lens[7] = 11, 1
+    sid = (np.arange(24) % 109).astype(np.int64)
+    names = ("x", "stats", "logw", "durations")
+    base = B200Session(str(voices("low_ms")))
+    ref = base.infer(ids, lens, (0.667, 1.0, 0.8), sid, seed=5, debug_tensors=names)
+    for env in ({"M3B200_ROWGEMM_NC": "128"}, {"M3B200_ROWGEMM_STAGES": "3"},
+                {"M3B200_ROWGEMM_NC": "128", "M3B200_ROWGEMM_STAGES": "3"}):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        alt_s = B200Session(str(voices("low_ms")))
+        alt = alt_s.infer(ids, lens, (0.667, 1.0, 0.8), sid, seed=5, debug_tensors=names)
+        for k in env:
+            monkeypatch.delenv(k)
+        for n in names:
+            np.testing.assert_array_equal(alt.tensors[n], ref.tensors[n], err_msg=f"{env}: {n}")
+        np.testing.assert_array_equal(alt.pcm, ref.pcm)
+        alt_s.close()
+    base.close()

@@ -15,7 +15,7 @@ if ! skip tests; then
   tail -5 $OUT/${TAG}_pytest.log
 fi
 if ! skip bench; then
-  timeout 300 python bench.py --steps 5 --warmup 3 > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err
+  timeout 300 python bench.py --steps 20 --warmup 3 > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err
   echo "bench exit $?"; cat $OUT/${TAG}_bench.json
 fi
 if ! skip launches; then
@@ -25,7 +25,7 @@ if ! skip launches; then
 fi
 if ! skip full; then
   timeout 300 ncu --set full --clock-control none --import-source on \
-    -k regex:'dec_fused_kernel|mrf_ws_kernel|mrf_tc_kernel' -c 3 -f -o $OUT/${TAG}_full \
+    -k regex:"${FULL_K:-dec_fused_kernel|mrf_ws_kernel|mrf_tc_kernel}" -c ${FULL_C:-3} -f -o $OUT/${TAG}_full \
     python bench.py --batch 64 --steps 1 --warmup 0 --profile-only > $OUT/${TAG}_full.log 2>&1
   echo "ncu full exit $?"
   ncu -i $OUT/${TAG}_full.ncu-rep --page raw --csv > $OUT/${TAG}_full_raw.csv 2>/dev/null
