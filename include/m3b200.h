@@ -77,6 +77,37 @@ int32_t m3_voice_get_info(const m3_voice* voice, m3_voice_info* info);
 int32_t m3_infer(m3_voice* voice, const int64_t* ids, const int64_t* lengths, int32_t batch, int32_t t_stride,
                  const float* scales, const int64_t* sid, uint64_t seed, uint32_t flags, m3_result** out);
 
+/* Per-utterance settings and the PCM post chain of one call (all members optional; zero-initialise,
+ * then set struct_size = sizeof(m3_infer_opts)).  This is what lets ONE engine call serve all sentences
+ * that Mimic3TextToSpeechSystem.end_utterance() speaks one by one (mimic3_tts/tts.py:470-515): each
+ * sentence carries its own Mimic3Settings (length_scale / noise_scale / noise_w / rate / volume,
+ * tts.py:519-543) and is separated from its neighbours by the silence of add_break (tts.py:452-465). */
+typedef struct m3_infer_opts {
+  uint32_t struct_size;          /* sizeof(m3_infer_opts) of the caller's header (ABI versioning)           */
+  uint32_t flags;                /* M3_FLAG_*                                                                */
+  uint64_t seed;                 /* Philox noise stream                                                      */
+  const float* row_scales;       /* [batch][3] {noise_scale, length_scale, noise_w} per utterance, or NULL:
+                                    the `scales` argument applies to every row (voice.py:182-189)           */
+  const double* volume;          /* [batch] audioop.mul(audio, 2, volume/100) factor (tts.py:540-543) or NULL */
+  const int64_t* lead_silence;   /* [batch] zero samples inserted before utterance b (tts.py:452-465) or NULL */
+  const int64_t* trail_silence;  /* [batch] zero samples appended after utterance b, or NULL                  */
+  int32_t wav_header;            /* != 0: m3_result_stream() starts with the 44-byte RIFF/WAVE header that
+                                    AudioResult.to_wav_bytes writes (opentts_abc/__init__.py:117-127)        */
+  int32_t reserved;
+} m3_infer_opts;
+
+/* m3_infer with per-utterance settings and the on-device PCM post chain.  `scales` may be NULL when
+ * opts->row_scales is given.  With silence, m3_result_sample_offsets()[b] is where utterance b's own
+ * samples start inside the output stream (its length is num_frames[b] * hop_length) and
+ * offsets[batch] is the total number of stream samples.  M3_FLAG_KEEP_FLOAT is rejected together with
+ * volume / silence / wav_header. */
+int32_t m3_infer_ex(m3_voice* voice, const int64_t* ids, const int64_t* lengths, int32_t batch, int32_t t_stride,
+                    const float* scales, const int64_t* sid, const m3_infer_opts* opts, m3_result** out);
+/* The output stream as bytes: [WAV header if asked][int16 LE samples, silences included]; host memory. */
+const uint8_t* m3_result_stream(const m3_result* r, int64_t* n_bytes);
+/* Host helper: the 44-byte header of 16-bit mono PCM at `sample_rate` with `n_samples` samples. */
+int32_t m3_wav_header(int32_t sample_rate, int64_t n_samples, uint8_t out[44]);
+
 int32_t m3_result_batch(const m3_result* r);
 /* sample_offsets[batch+1]: utterance b occupies [off[b], off[b+1]) of the packed buffers. */
 const int64_t* m3_result_sample_offsets(const m3_result* r);

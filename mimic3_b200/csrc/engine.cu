@@ -916,15 +916,53 @@ struct Run {
 
 }  // namespace
 
+void write_wav_header(uint8_t* h, int sample_rate, int64_t n_samples) {
+  const uint32_t data = uint32_t(n_samples * 2);
+  auto u32 = [&](int o, uint32_t v) {
+    for (int i = 0; i < 4; ++i) h[o + i] = uint8_t(v >> (8 * i));
+  };
+  auto u16 = [&](int o, uint32_t v) {
+    h[o] = uint8_t(v);
+    h[o + 1] = uint8_t(v >> 8);
+  };
+  memcpy(h, "RIFF", 4);
+  u32(4, 36u + data);
+  memcpy(h + 8, "WAVEfmt ", 8);
+  u32(16, 16u);
+  u16(20, 1u);   // PCM
+  u16(22, 1u);   // mono
+  u32(24, uint32_t(sample_rate));
+  u32(28, uint32_t(sample_rate) * 2u);
+  u16(32, 2u);   // block align
+  u16(34, 16u);  // bits per sample
+  memcpy(h + 36, "data", 4);
+  u32(40, data);
+}
+
 Result* run_inference(Voice& v, const int64_t* ids, const int64_t* lengths, int batch, int t_stride,
-                      const float* scales, const int64_t* sid, uint64_t seed, uint32_t flags) {
+                      const float* scales, const int64_t* sid, uint64_t seed, uint32_t flags, const InferOpts* opts) {
   DeviceVoice& dv = *v.dv;
   const VoiceConfig& c = dv.cfg;
+  const InferOpts no_opts;
+  const InferOpts& o = opts ? *opts : no_opts;
   if (batch <= 0) throw EngineError(M3_ERR_INVALID, "batch must be >= 1");
-  if (!ids || !lengths || !scales) throw EngineError(M3_ERR_INVALID, "ids, lengths and scales must not be NULL");
+  if (!ids || !lengths) throw EngineError(M3_ERR_INVALID, "ids and lengths must not be NULL");
+  if (!scales && !o.row_scales) throw EngineError(M3_ERR_INVALID, "scales (or per-utterance row_scales) must not be NULL");
   if (t_stride <= 0) throw EngineError(M3_ERR_INVALID, "input has zero phonemes");
   if (dv.has_emb_g && !sid) throw EngineError(M3_ERR_INVALID, "multi-speaker voice: input 'sid' is required");
-  const float noise_scale = scales[0], length_scale = scales[1], noise_w = scales[2];
+  const bool post = o.post_chain();
+  if (post && (flags & M3_FLAG_KEEP_FLOAT))
+    throw EngineError(M3_ERR_INVALID, "M3_FLAG_KEEP_FLOAT cannot be combined with the PCM post chain (volume / silence / WAV)");
+  for (int b = 0; b < batch; ++b) {
+    if (o.row_scales)
+      for (int k = 0; k < 3; ++k)
+        if (!std::isfinite(o.row_scales[3 * b + k]))
+          throw EngineError(M3_ERR_INVALID, "row_scales[" + std::to_string(b) + "] is not finite");
+    if (o.volume && !std::isfinite(o.volume[b])) throw EngineError(M3_ERR_INVALID, "volume[" + std::to_string(b) + "] is not finite");
+    if ((o.lead_silence && o.lead_silence[b] < 0) || (o.trail_silence && o.trail_silence[b] < 0))
+      throw EngineError(M3_ERR_INVALID, "silence[" + std::to_string(b) + "] is negative");
+  }
+  const float noise_scale = scales ? scales[0] : 0.f, length_scale = scales ? scales[1] : 1.f, noise_w = scales ? scales[2] : 0.f;
   const bool ids_on_device = flags & M3_FLAG_DEVICE_IDS;
 
   std::vector<int> tok_off(batch), tok_len(batch);
@@ -1013,6 +1051,15 @@ Result* run_inference(Voice& v, const int64_t* ids, const int64_t* lengths, int 
     memcpy(cx.h_in.p, ids, size_t(batch) * t_stride * 8);
     M3_CUDA(cudaMemcpyAsync(d_ids, cx.h_in.p, size_t(batch) * t_stride * 8, cudaMemcpyHostToDevice, st));
   }
+  // per-utterance settings (Mimic3Settings of each sentence, tts.py:519-528): staged once, read by the
+  // noise / duration / prior kernels instead of the scalar scales
+  float* d_row_scales = nullptr;
+  cx.h_opts.reserve(size_t(batch) * (3 * sizeof(float) + sizeof(long long) + sizeof(double)) + 64);
+  if (o.row_scales) {
+    d_row_scales = A.alloc<float>(size_t(batch) * 3);
+    memcpy(cx.h_opts.p, o.row_scales, size_t(batch) * 3 * sizeof(float));
+    M3_CUDA(cudaMemcpyAsync(d_row_scales, cx.h_opts.p, size_t(batch) * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
+  }
   Segs tok{d_tok_off, d_tok_len, batch, Tmax};
   Segs one{d_one, d_one + 1, 1, batch};
   {
@@ -1078,7 +1125,7 @@ Result* run_inference(Voice& v, const int64_t* ids, const int64_t* lengths, int 
     R.row_conv(dv.dp_proj, h, Fd, t1, Fd);
     float* hc = t1;  // conditioning for the conv flows
     float* s1 = h;   // h is free now: reuse as scratch
-    launch_sdp_noise(z, noise_w, seed, d_tok_off, d_tok_len, batch, Tmax, st);
+    launch_sdp_noise(z, noise_w, d_row_scales, seed, d_tok_off, d_tok_len, batch, Tmax, st);
     // z channels are never moved: `c0` tracks which physical column is logical channel 0
     int c0 = 0;
     const float inv_sqrt = 1.0f / sqrtf(float(Fd));
@@ -1120,7 +1167,7 @@ Result* run_inference(Voice& v, const int64_t* ids, const int64_t* lengths, int 
   // ---------------- A.0 durations -> frames ----------------
   R.mark("duration_predictor");
   int* cum = A.alloc<int>(NT);
-  launch_durations(logw, 1, length_scale, cum, d_frm_len, d_tok_off, d_tok_len, batch, st);
+  launch_durations(logw, 1, length_scale, d_row_scales, cum, d_frm_len, d_tok_off, d_tok_len, batch, st);
   int* h_frames = hm + 2 * batch;
   M3_CUDA(cudaMemcpyAsync(h_frames, d_frm_len, size_t(batch) * sizeof(int), cudaMemcpyDeviceToHost, st));
   M3_CUDA(cudaStreamSynchronize(st));
@@ -1138,8 +1185,16 @@ Result* run_inference(Voice& v, const int64_t* ids, const int64_t* lengths, int 
     throw EngineError(M3_ERR_INVALID, "batch produces more than 2^31 samples; split the batch");
   res->frames.assign(frm_len.begin(), frm_len.end());
   res->sample_off.resize(batch + 1);
-  for (int b = 0; b < batch; ++b) res->sample_off[b] = int64_t(frm_off[b]) * hop;
-  res->sample_off[batch] = NF * hop;
+  int64_t stream_samples = 0;  // output stream: [lead silence][utterance][trail silence] per row
+  for (int b = 0; b < batch; ++b) {
+    if (o.lead_silence) stream_samples += o.lead_silence[b];
+    res->sample_off[b] = stream_samples;
+    stream_samples += int64_t(frm_len[b]) * hop;
+    if (o.trail_silence) stream_samples += o.trail_silence[b];
+  }
+  res->sample_off[batch] = stream_samples;
+  if (stream_samples > (int64_t(1) << 31) - 64)
+    throw EngineError(M3_ERR_INVALID, "batch produces more than 2^31 output samples; split the batch");
   memcpy(hm + 2 * batch, frm_off.data(), batch * sizeof(int));
   memcpy(hm + 3 * batch, frm_len.data(), batch * sizeof(int));
   M3_CUDA(cudaMemcpyAsync(d_frm_off, hm + 2 * batch, size_t(batch) * 2 * sizeof(int), cudaMemcpyHostToDevice, st));
@@ -1170,7 +1225,7 @@ Result* run_inference(Voice& v, const int64_t* ids, const int64_t* lengths, int 
       fl += size_t(NF) * scale * dv.ups[i].cout * 5;  // x, y0, y1, tmp, sum
     }
     fl += size_t(NF) * hop;                 // audio
-    size_t bytes = fl * 4 + size_t(NF) * hop * 2 + size_t(batch) * 16 + (1 << 16) + 512 * 64;
+    size_t bytes = fl * 4 + size_t(stream_samples) * 2 + size_t(batch) * 32 + (1 << 16) + 512 * 64;
     cx.a2.reserve(bytes);
   }
   Arena& A2 = cx.a2;
@@ -1178,7 +1233,7 @@ Result* run_inference(Voice& v, const int64_t* ids, const int64_t* lengths, int 
   // ---------------- length regulator + prior sample ----------------
   float* z = A2.alloc<float>(size_t(NF) * I);
   R.mark("durations_sync");
-  launch_expand(stats, I, cum, d_tok_off, d_tok_len, d_frm_off, d_frm_len, batch, Fmax, noise_scale, seed, z, st);
+  launch_expand(stats, I, cum, d_tok_off, d_tok_len, d_frm_off, d_frm_len, batch, Fmax, noise_scale, d_row_scales, seed, z, st);
   R.mark("expand");
   R.dump("z_p", z, NF, I);
 
@@ -1302,7 +1357,7 @@ Result* run_inference(Voice& v, const int64_t* ids, const int64_t* lengths, int 
   const int nk = int(c.rb_kernels.size());
   const bool fuse_last = dv.use_tc && dv.dec_last.ok && !getenv("M3B200_UNFUSED_DEC");
   float* audio = A2.alloc<float>(size_t(NF) * hop);
-  int16_t* pcm = A2.alloc<int16_t>(size_t(NF) * hop);
+  int16_t* pcm = A2.alloc<int16_t>(size_t(stream_samples));
   unsigned* peak = A2.alloc<unsigned>(batch);
   M3_CUDA(cudaMemsetAsync(peak, 0, size_t(batch) * 4, st));
   bool audio_done = false;
@@ -1541,18 +1596,40 @@ Result* run_inference(Voice& v, const int64_t* ids, const int64_t* lengths, int 
   }
   if (!audio_done)
     launch_conv_post(cur, dv.post_c, dv.post_w, dv.post_k, 0.01f, audio, peak, d_frm_off, d_frm_len, hop, batch, Fmax, st);
-  launch_to_int16(audio, peak, pcm, d_frm_off, d_frm_len, hop, batch, Fmax, st);
+  if (!post) {
+    launch_to_int16(audio, peak, pcm, d_frm_off, d_frm_len, hop, batch, Fmax, st);
+  } else {
+    // PCM post chain on the device: volume, inter-sentence silence, WAV framing
+    long long* d_out_off = A2.alloc<long long>(batch);
+    double* d_volume = o.volume ? A2.alloc<double>(batch) : nullptr;
+    char* hp = static_cast<char*>(cx.h_opts.p) + ((size_t(batch) * 3 * sizeof(float) + 15) & ~size_t(15));
+    long long* h_off = reinterpret_cast<long long*>(hp);
+    double* h_vol = reinterpret_cast<double*>(hp + size_t(batch) * sizeof(long long));
+    for (int b = 0; b < batch; ++b) h_off[b] = res->sample_off[b];
+    M3_CUDA(cudaMemcpyAsync(d_out_off, h_off, size_t(batch) * sizeof(long long), cudaMemcpyHostToDevice, st));
+    if (o.volume) {
+      memcpy(h_vol, o.volume, size_t(batch) * sizeof(double));
+      M3_CUDA(cudaMemcpyAsync(d_volume, h_vol, size_t(batch) * sizeof(double), cudaMemcpyHostToDevice, st));
+    }
+    if (stream_samples != NF * hop) M3_CUDA(cudaMemsetAsync(pcm, 0, size_t(stream_samples) * 2, st));
+    launch_to_int16_post(audio, peak, pcm, d_frm_off, d_frm_len, hop, d_out_off, d_volume, batch, Fmax, st);
+  }
   R.mark("post_int16");
 
   // ---------------- outputs ----------------
-  const size_t NS = size_t(NF) * hop;
+  const size_t NS = size_t(stream_samples);
+  const size_t hdr = o.wav_header ? 44 : 0;
   res->d_pcm = pcm;
   float* h_peaks = reinterpret_cast<float*>(hm);  // reuse meta staging (tok arrays no longer needed on host)
   M3_CUDA(cudaMemcpyAsync(h_peaks, peak, size_t(batch) * 4, cudaMemcpyDeviceToHost, st));
   if (!(flags & M3_FLAG_NO_HOST_COPY)) {
-    cx.h_pcm.reserve(NS * 2);
-    M3_CUDA(cudaMemcpyAsync(cx.h_pcm.p, pcm, NS * 2, cudaMemcpyDeviceToHost, st));
-    res->pcm = static_cast<const int16_t*>(cx.h_pcm.p);
+    cx.h_pcm.reserve(hdr + NS * 2);
+    uint8_t* hs = static_cast<uint8_t*>(cx.h_pcm.p);
+    if (hdr) write_wav_header(hs, c.sample_rate, int64_t(NS));
+    M3_CUDA(cudaMemcpyAsync(hs + hdr, pcm, NS * 2, cudaMemcpyDeviceToHost, st));
+    res->pcm = reinterpret_cast<const int16_t*>(hs + hdr);
+    res->stream = hs;
+    res->stream_bytes = int64_t(hdr + NS * 2);
     if (flags & M3_FLAG_KEEP_FLOAT) {
       cx.h_audio.reserve(NS * 4);
       M3_CUDA(cudaMemcpyAsync(cx.h_audio.p, audio, NS * 4, cudaMemcpyDeviceToHost, st));

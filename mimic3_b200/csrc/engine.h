@@ -184,7 +184,7 @@ struct Context {  // per concurrent call: stream + workspaces (SURVEY.md §8b th
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   Arena a1, a2;
-  PinnedBuf h_in, h_meta, h_pcm, h_audio;
+  PinnedBuf h_in, h_meta, h_pcm, h_audio, h_opts;
   std::vector<cudaEvent_t> marks;  // stage-timing events (M3_FLAG_STAGE_TIMING), created lazily
   explicit Context(int dev);
   ~Context();
@@ -200,6 +200,8 @@ struct Result {
   std::vector<int64_t> sample_off, frames;
   std::vector<float> peaks;
   const int16_t* pcm = nullptr;   // pinned, owned by ctx
+  const uint8_t* stream = nullptr;  // pinned: [44-byte WAV header if asked] + pcm (silences included)
+  int64_t stream_bytes = 0;
   const float* audio = nullptr;   // pinned, owned by ctx
   const void* d_pcm = nullptr;    // device, owned by ctx
   double device_ms = 0;
@@ -218,7 +220,23 @@ struct Voice {
   void release(Context* c);
 };
 
+// Per-utterance settings and the PCM post chain (m3_infer_opts in include/m3b200.h); all optional.
+struct InferOpts {
+  const float* row_scales = nullptr;     // [batch][3] {noise_scale, length_scale, noise_w}
+  const double* volume = nullptr;        // [batch] audioop.mul factor
+  const int64_t* lead_silence = nullptr;   // [batch] zero samples before utterance b
+  const int64_t* trail_silence = nullptr;  // [batch] zero samples after utterance b
+  int sample_rate_override = 0;
+  bool wav_header = false;
+  bool post_chain() const { return volume || lead_silence || trail_silence || wav_header; }
+};
+
+// 44-byte RIFF/WAVE header of 16-bit mono PCM (what Python's wave module writes for
+// opentts_abc.AudioResult.to_wav_bytes, opentts_abc/__init__.py:117-127)
+void write_wav_header(uint8_t* out44, int sample_rate, int64_t n_samples);
+
 Result* run_inference(Voice& v, const int64_t* ids, const int64_t* lengths, int batch, int t_stride,
-                      const float* scales, const int64_t* sid, uint64_t seed, uint32_t flags);
+                      const float* scales, const int64_t* sid, uint64_t seed, uint32_t flags,
+                      const InferOpts* opts = nullptr);
 
 }  // namespace m3

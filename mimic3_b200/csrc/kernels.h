@@ -252,17 +252,18 @@ void launch_convflow_pre(const float* z, int zc, const float* w, const float* b,
 // z[t][zc] = RQS^-1(z[t][zc] | params[t][0:29] scaled)
 void launch_rqs_inverse(float* z, int zc, const float* params, int pstride, float inv_sqrt_c, int rows,
                         cudaStream_t st);
-void launch_sdp_noise(float* z, float noise_w, uint64_t seed, const int* seg_off, const int* seg_len, int n_seg,
-                      int max_len, cudaStream_t st);
+// row_scales (nullable, here and below): per-utterance [noise_scale, length_scale, noise_w] overriding the scalar
+void launch_sdp_noise(float* z, float noise_w, const float* row_scales, uint64_t seed, const int* seg_off,
+                      const int* seg_len, int n_seg, int max_len, cudaStream_t st);
 // logw = (z[:, zc] - m) * exp(-logs)
 void launch_sdp_finish(const float* z, int zc, float m, float logs, float* logw, int rows, cudaStream_t st);
 // durations: w_ceil = ceil(exp(logw)*length_scale); cum = inclusive scan per utterance; frames[b] = max(1, total)
-void launch_durations(const float* logw, int logw_stride, float length_scale, int* cum, int* frames,
-                      const int* seg_off, const int* seg_len, int n_seg, cudaStream_t st);
+void launch_durations(const float* logw, int logw_stride, float length_scale, const float* row_scales, int* cum,
+                      int* frames, const int* seg_off, const int* seg_len, int n_seg, cudaStream_t st);
 // z_p[frame][c] = m[tok][c] + N(0,1)*exp(logs[tok][c])*noise_scale  (stats = [m | logs], stride 2I)
 void launch_expand(const float* stats, int I, const int* cum, const int* tok_off, const int* tok_len,
                    const int* frm_off, const int* frm_len, int n_seg, int max_frames, float noise_scale,
-                   uint64_t seed, float* zp, cudaStream_t st);
+                   const float* row_scales, uint64_t seed, float* zp, cudaStream_t st);
 void launch_flip_channels(float* x, int rows, int C, cudaStream_t st);
 // y = tanh(conv_k(lrelu(x, slope)))  (C_out = 1, no bias) + per-utterance max|y|
 void launch_conv_post(const float* x, int C, const float* w /*[k][C]*/, int k, float slope, float* audio,
@@ -271,5 +272,10 @@ void launch_conv_post(const float* x, int C, const float* w /*[k][C]*/, int k, f
 // pcm = trunc(clip(audio * 32767/max(0.01, peak)))  (mimic3_tts/utils.py:237-244)
 void launch_to_int16(const float* audio, const unsigned* peak_bits, int16_t* pcm, const int* seg_off,
                      const int* seg_len, int scale, int n_seg, int max_len, cudaStream_t st);
+// same + the PCM post chain (tts.py:536-543): utterance b written at out_off[b] of `stream`, optional
+// audioop.mul volume factor per utterance
+void launch_to_int16_post(const float* audio, const unsigned* peak_bits, int16_t* stream, const int* seg_off,
+                          const int* seg_len, int scale, const long long* out_off, const double* volume, int n_seg,
+                          int max_len, cudaStream_t st);
 
 }  // namespace m3

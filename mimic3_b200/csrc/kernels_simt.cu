@@ -836,20 +836,22 @@ void launch_rqs_inverse(float* z, int zc, const float* params, int pstride, floa
   M3_LAUNCHED();
 }
 
-__global__ void sdp_noise_kernel(float* z, float noise_w, uint64_t seed, const int* seg_off, const int* seg_len) {
+__global__ void sdp_noise_kernel(float* z, float noise_w, const float* __restrict__ row_scales, uint64_t seed,
+                                 const int* seg_off, const int* seg_len) {
   const int seg = blockIdx.y;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= seg_len[seg]) return;
+  if (row_scales) noise_w = row_scales[seg * 3 + 2];
   const long long row = seg_off[seg] + t;
 #pragma unroll
   for (int c = 0; c < 2; ++c)
     z[row * 2 + c] = noise_w != 0.f ? philox_normal(seed, 0u, uint32_t(seg), uint32_t(t), uint32_t(c)) * noise_w : 0.f;
 }
 
-void launch_sdp_noise(float* z, float noise_w, uint64_t seed, const int* seg_off, const int* seg_len, int n_seg,
-                      int max_len, cudaStream_t st) {
+void launch_sdp_noise(float* z, float noise_w, const float* row_scales, uint64_t seed, const int* seg_off,
+                      const int* seg_len, int n_seg, int max_len, cudaStream_t st) {
   if (max_len <= 0) return;
-  sdp_noise_kernel<<<dim3((max_len + 127) / 128, n_seg), 128, 0, st>>>(z, noise_w, seed, seg_off, seg_len);
+  sdp_noise_kernel<<<dim3((max_len + 127) / 128, n_seg), 128, 0, st>>>(z, noise_w, row_scales, seed, seg_off, seg_len);
   M3_LAUNCHED();
 }
 
@@ -869,10 +871,12 @@ void launch_sdp_finish(const float* z, int zc, float m, float logs, float* logw,
 // Durations -> monotonic alignment -> expanded prior
 // -------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) durations_kernel(const float* __restrict__ logw, int logw_stride,
-                                                        float length_scale, int* cum, int* frames,
-                                                        const int* seg_off, const int* seg_len) {
+                                                        float length_scale, const float* __restrict__ row_scales,
+                                                        int* cum, int* frames, const int* seg_off,
+                                                        const int* seg_len) {
   const int seg = blockIdx.x;
   const int T = seg_len[seg];
+  if (row_scales) length_scale = row_scales[seg * 3 + 1];
   const long long base = seg_off[seg];
   __shared__ int warp_tot[8];
   __shared__ int carry_s;
@@ -905,18 +909,20 @@ __global__ void __launch_bounds__(256) durations_kernel(const float* __restrict_
   if (threadIdx.x == 0) frames[seg] = max(1, carry_s);
 }
 
-void launch_durations(const float* logw, int logw_stride, float length_scale, int* cum, int* frames,
-                      const int* seg_off, const int* seg_len, int n_seg, cudaStream_t st) {
+void launch_durations(const float* logw, int logw_stride, float length_scale, const float* row_scales, int* cum,
+                      int* frames, const int* seg_off, const int* seg_len, int n_seg, cudaStream_t st) {
   if (n_seg <= 0) return;
-  durations_kernel<<<n_seg, 256, 0, st>>>(logw, logw_stride, length_scale, cum, frames, seg_off, seg_len);
+  durations_kernel<<<n_seg, 256, 0, st>>>(logw, logw_stride, length_scale, row_scales, cum, frames, seg_off, seg_len);
   M3_LAUNCHED();
 }
 
 __global__ void __launch_bounds__(256) expand_kernel(const float* __restrict__ stats, int I,
                                                      const int* __restrict__ cum, const int* tok_off,
                                                      const int* tok_len, const int* frm_off, const int* frm_len,
-                                                     float noise_scale, uint64_t seed, float* zp) {
+                                                     float noise_scale, const float* __restrict__ row_scales,
+                                                     uint64_t seed, float* zp) {
   const int seg = blockIdx.y;
+  if (row_scales) noise_scale = row_scales[seg * 3];
   const int F = frm_len[seg];
   const int y = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -946,10 +952,10 @@ __global__ void __launch_bounds__(256) expand_kernel(const float* __restrict__ s
 
 void launch_expand(const float* stats, int I, const int* cum, const int* tok_off, const int* tok_len,
                    const int* frm_off, const int* frm_len, int n_seg, int max_frames, float noise_scale,
-                   uint64_t seed, float* zp, cudaStream_t st) {
+                   const float* row_scales, uint64_t seed, float* zp, cudaStream_t st) {
   if (max_frames <= 0) return;
   expand_kernel<<<dim3((max_frames + 7) / 8, n_seg), 256, 0, st>>>(stats, I, cum, tok_off, tok_len, frm_off,
-                                                                     frm_len, noise_scale, seed, zp);
+                                                                     frm_len, noise_scale, row_scales, seed, zp);
   M3_LAUNCHED();
 }
 
@@ -1060,6 +1066,42 @@ void launch_to_int16(const float* audio, const unsigned* peak_bits, int16_t* pcm
   if (max_len <= 0) return;
   to_int16_kernel<<<dim3((max_len * scale + 255) / 256, n_seg), 256, 0, st>>>(audio, peak_bits, pcm, seg_off,
                                                                               seg_len, scale);
+  M3_LAUNCHED();
+}
+
+// int16 conversion + the PCM post chain of Mimic3TextToSpeechSystem._speak_sentence_phonemes
+// (mimic3_tts/tts.py:536-543): utterance b lands at out_off[b] of the output stream (the gaps are the
+// silences of add_break, tts.py:452-465, zero-filled by the caller) and, when volume != NULL, goes through
+// audioop.mul(bytes, 2, factor): val = sample * factor in double; > 32767 -> 32767; < -32767 -> -32768;
+// floor.  (CPython Modules/audioop.c, fbound(); pinned against the real module in tests/test_post_chain.py.)
+__global__ void to_int16_post_kernel(const float* __restrict__ audio, const unsigned* __restrict__ peak_bits,
+                                     int16_t* stream, const int* seg_off, const int* seg_len, int scale,
+                                     const long long* __restrict__ out_off, const double* __restrict__ volume) {
+  const int seg = blockIdx.y;
+  const int L = seg_len[seg] * scale;
+  const long long base = (long long)seg_off[seg] * scale;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= L) return;
+  const float peak = fmaxf(0.01f, __uint_as_float(peak_bits[seg]));
+  const float s = __fdiv_rn(32767.0f, peak);
+  float y = __fmul_rn(audio[base + t], s);
+  y = fminf(fmaxf(y, -32767.0f), 32767.0f);
+  int v = int(y);
+  if (volume) {
+    double d = __dmul_rn(double(v), volume[seg]);
+    if (d > 32767.0) d = 32767.0;
+    else if (d < -32767.0) d = -32768.0;
+    v = int(floor(d));
+  }
+  stream[out_off[seg] + t] = int16_t(v);
+}
+
+void launch_to_int16_post(const float* audio, const unsigned* peak_bits, int16_t* stream, const int* seg_off,
+                          const int* seg_len, int scale, const long long* out_off, const double* volume, int n_seg,
+                          int max_len, cudaStream_t st) {
+  if (max_len <= 0) return;
+  to_int16_post_kernel<<<dim3((max_len * scale + 255) / 256, n_seg), 256, 0, st>>>(audio, peak_bits, stream, seg_off,
+                                                                                   seg_len, scale, out_off, volume);
   M3_LAUNCHED();
 }
 

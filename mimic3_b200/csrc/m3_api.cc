@@ -1,6 +1,7 @@
 // C ABI of libm3b200.so (declared in include/m3b200.h).
 #include <cuda_runtime.h>
 
+#include <cstddef>
 #include <cstring>
 #include <string>
 
@@ -108,6 +109,44 @@ int32_t m3_infer(m3_voice* voice, const int64_t* ids, const int64_t* lengths, in
     mr->r = r;
     *out = mr;
   });
+}
+
+int32_t m3_infer_ex(m3_voice* voice, const int64_t* ids, const int64_t* lengths, int32_t batch, int32_t t_stride,
+                    const float* scales, const int64_t* sid, const m3_infer_opts* opts, m3_result** out) {
+  if (!voice || !out) return fail(M3_ERR_INVALID, "m3_infer_ex: NULL argument");
+  *out = nullptr;
+  if (opts && opts->struct_size < offsetof(m3_infer_opts, reserved))
+    return fail(M3_ERR_INVALID, "m3_infer_ex: opts->struct_size does not describe an m3_infer_opts");
+  return guarded([&] {
+    m3::InferOpts o;
+    uint64_t seed = 0;
+    uint32_t flags = 0;
+    if (opts) {
+      o.row_scales = opts->row_scales;
+      o.volume = opts->volume;
+      o.lead_silence = opts->lead_silence;
+      o.trail_silence = opts->trail_silence;
+      o.wav_header = opts->wav_header != 0;
+      seed = opts->seed;
+      flags = opts->flags;
+    }
+    m3::Result* r = m3::run_inference(voice->v, ids, lengths, batch, t_stride, scales, sid, seed, flags, &o);
+    m3_result* mr = new m3_result();
+    mr->r = r;
+    *out = mr;
+  });
+}
+
+const uint8_t* m3_result_stream(const m3_result* r, int64_t* n_bytes) {
+  if (n_bytes) *n_bytes = r ? r->r->stream_bytes : 0;
+  return r ? r->r->stream : nullptr;
+}
+
+int32_t m3_wav_header(int32_t sample_rate, int64_t n_samples, uint8_t out[44]) {
+  if (!out || sample_rate <= 0 || n_samples < 0 || n_samples > ((int64_t(1) << 31) - 64))
+    return fail(M3_ERR_INVALID, "m3_wav_header: bad argument");
+  m3::write_wav_header(out, sample_rate, n_samples);
+  return M3_OK;
 }
 
 int32_t m3_result_batch(const m3_result* r) { return r ? r->r->batch : 0; }

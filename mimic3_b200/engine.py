@@ -32,6 +32,7 @@ API_SYMBOLS = [
     "m3_result_num_frames", "m3_result_pcm", "m3_result_audio", "m3_result_peaks",
     "m3_result_device_pcm", "m3_result_device_ms", "m3_result_kernel_launches",
     "m3_result_tensor", "m3_result_free", "m3_selftest",
+    "m3_infer_ex", "m3_result_stream", "m3_wav_header",
 ]
 
 
@@ -46,6 +47,16 @@ class VoiceInfo(C.Structure):
         ("hidden_channels", C.c_int32), ("inter_channels", C.c_int32),
         ("noise_scale", C.c_float), ("length_scale", C.c_float), ("noise_w", C.c_float),
         ("n_params", C.c_int64), ("device", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+class InferOpts(C.Structure):
+    """``m3_infer_opts`` (include/m3b200.h): per-utterance settings + the PCM post chain."""
+    _fields_ = [
+        ("struct_size", C.c_uint32), ("flags", C.c_uint32), ("seed", C.c_uint64),
+        ("row_scales", C.POINTER(C.c_float)), ("volume", C.POINTER(C.c_double)),
+        ("lead_silence", C.POINTER(C.c_int64)), ("trail_silence", C.POINTER(C.c_int64)),
+        ("wav_header", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -79,6 +90,13 @@ def load_library() -> C.CDLL:
         lib.m3_infer.restype = i32
         lib.m3_infer.argtypes = [vp, vp, i64p, i32, i32, C.POINTER(C.c_float), i64p, C.c_uint64,
                                  C.c_uint32, C.POINTER(vp)]
+        lib.m3_infer_ex.restype = i32
+        lib.m3_infer_ex.argtypes = [vp, vp, i64p, i32, i32, C.POINTER(C.c_float), i64p, C.POINTER(InferOpts),
+                                    C.POINTER(vp)]
+        lib.m3_result_stream.restype = C.POINTER(C.c_uint8)
+        lib.m3_result_stream.argtypes = [vp, i64p]
+        lib.m3_wav_header.restype = i32
+        lib.m3_wav_header.argtypes = [i32, C.c_int64, C.POINTER(C.c_uint8)]
         lib.m3_result_batch.restype = i32
         lib.m3_result_batch.argtypes = [vp]
         for name, rt in (("m3_result_sample_offsets", i64p), ("m3_result_num_frames", i64p),
@@ -114,8 +132,8 @@ class InferenceResult:
     ``infer(..., copy=False)`` they are zero-copy views of the engine's pinned host buffers, valid
     until ``close()`` (which turns them into copies and returns the buffers to the engine's pool)."""
 
-    __slots__ = ("pcm", "audio", "sample_offsets", "frames", "peaks", "device_ms", "launches",
-                 "tensors", "device_pcm_ptr", "_lib", "_res")
+    __slots__ = ("pcm", "audio", "stream", "sample_offsets", "frames", "peaks", "device_ms", "launches",
+                 "tensors", "device_pcm_ptr", "hop_length", "_lib", "_res")
 
     def detach(self):
         """Turn the views into owned copies and release the engine buffers."""
@@ -123,13 +141,14 @@ class InferenceResult:
         if res:
             self.pcm = None if self.pcm is None else self.pcm.copy()
             self.audio = None if self.audio is None else self.audio.copy()
+            self.stream = None if self.stream is None else self.stream.copy()
             self._lib.m3_result_free(res)
 
     def close(self):
         """Release the engine buffers; zero-copy views become invalid and are dropped."""
         res, self._res = getattr(self, "_res", None), None
         if res:
-            self.pcm = self.audio = None
+            self.pcm = self.audio = self.stream = None
             self._lib.m3_result_free(res)
 
     def __del__(self):  # pragma: no cover
@@ -141,10 +160,17 @@ class InferenceResult:
                 pass
 
     def utterance_pcm(self, b: int) -> np.ndarray:
-        return self.pcm[self.sample_offsets[b]:self.sample_offsets[b + 1]]
+        """Utterance b's own samples (silences of the post chain, if any, lie between utterances)."""
+        lo = int(self.sample_offsets[b])
+        return self.pcm[lo:lo + int(self.frames[b]) * self.hop_length]
 
     def utterance_audio(self, b: int) -> np.ndarray:
-        return self.audio[self.sample_offsets[b]:self.sample_offsets[b + 1]]
+        lo = int(self.sample_offsets[b])
+        return self.audio[lo:lo + int(self.frames[b]) * self.hop_length]
+
+    def stream_bytes(self) -> bytes:
+        """[WAV header if asked] + all samples with their silences, as Python bytes."""
+        return self.stream.tobytes() if self.stream is not None else self.pcm.tobytes()
 
     @property
     def total_samples(self) -> int:
@@ -184,11 +210,18 @@ class B200Session:
               sid: Optional[np.ndarray] = None, seed: int = 0, keep_float: bool = False,
               debug_tensors: Sequence[str] = (), host_copy: bool = True,
               device_ids_ptr: Optional[int] = None, stage_timing: bool = False,
-              device_pcm_out=None, copy: bool = True) -> InferenceResult:
+              device_pcm_out=None, copy: bool = True, row_scales=None, volume=None, lead_silence=None,
+              trail_silence=None, wav_header: bool = False) -> InferenceResult:
         """``device_pcm_out``: optional torch int16 CUDA tensor; the packed PCM is copied into it on the
-        device (for NCCL gathers) before the engine's buffers are released."""
+        device (for NCCL gathers) before the engine's buffers are released.
+
+        ``row_scales`` (batch, 3) float32, ``volume`` (batch,) float64, ``lead_silence`` / ``trail_silence``
+        (batch,) int64 samples and ``wav_header`` select ``m3_infer_ex``: per-utterance settings and the
+        on-device PCM post chain of ``_speak_sentence_phonemes`` / ``add_break`` (tts.py:452-465, 519-543)."""
         lengths = np.ascontiguousarray(lengths, dtype=np.int64)
         batch = int(lengths.shape[0])
+        extended = (row_scales is not None or volume is not None or lead_silence is not None
+                    or trail_silence is not None or wav_header)
         flags = 0
         if device_ids_ptr is not None:
             ids_ptr = C.c_void_p(int(device_ids_ptr))
@@ -200,7 +233,7 @@ class B200Session:
                 raise ValueError("ids must be int64 (batch, T) matching input_lengths")
             t_stride = int(ids.shape[1])
             ids_ptr = ids.ctypes.data_as(C.c_void_p)
-        sc = (C.c_float * 3)(*[float(s) for s in scales])
+        sc = (C.c_float * 3)(*[float(s) for s in scales]) if scales is not None else None
         sid_p = None
         if sid is not None:
             sid = np.ascontiguousarray(sid, dtype=np.int64)
@@ -217,12 +250,41 @@ class B200Session:
         if not host_copy:
             flags |= FLAG_NO_HOST_COPY
         res = C.c_void_p()
-        rc = self._lib.m3_infer(self._h, ids_ptr, lengths.ctypes.data_as(C.POINTER(C.c_int64)), batch,
-                                t_stride, sc, sid_p, C.c_uint64(seed & (2 ** 64 - 1)), flags, C.byref(res))
+        if extended:
+            keep = []  # arrays must outlive the call
+
+            def arr(x, dtype, shape, what):
+                a = np.ascontiguousarray(x, dtype=dtype)
+                if a.shape != shape:
+                    raise ValueError(f"{what} must have shape {shape}")
+                keep.append(a)
+                return a
+            o = InferOpts()
+            o.struct_size = C.sizeof(InferOpts)
+            o.flags = flags
+            o.seed = seed & (2 ** 64 - 1)
+            if row_scales is not None:
+                o.row_scales = arr(row_scales, np.float32, (batch, 3), "row_scales").ctypes.data_as(C.POINTER(C.c_float))
+            if volume is not None:
+                o.volume = arr(volume, np.float64, (batch,), "volume").ctypes.data_as(C.POINTER(C.c_double))
+            if lead_silence is not None:
+                o.lead_silence = arr(lead_silence, np.int64, (batch,), "lead_silence").ctypes.data_as(C.POINTER(C.c_int64))
+            if trail_silence is not None:
+                o.trail_silence = arr(trail_silence, np.int64, (batch,), "trail_silence").ctypes.data_as(C.POINTER(C.c_int64))
+            o.wav_header = 1 if wav_header else 0
+            rc = self._lib.m3_infer_ex(self._h, ids_ptr, lengths.ctypes.data_as(C.POINTER(C.c_int64)), batch,
+                                       t_stride, sc, sid_p, C.byref(o), C.byref(res))
+        else:
+            if sc is None:
+                raise ValueError("scales are required (or pass row_scales)")
+            rc = self._lib.m3_infer(self._h, ids_ptr, lengths.ctypes.data_as(C.POINTER(C.c_int64)), batch,
+                                    t_stride, sc, sid_p, C.c_uint64(seed & (2 ** 64 - 1)), flags, C.byref(res))
         if rc != M3_OK:
             _raise(self._lib, rc)
         out = InferenceResult()
         out._lib, out._res = self._lib, res
+        out.hop_length = int(self.info.hop_length)
+        out.stream = None
         if True:
             off = np.ctypeslib.as_array(self._lib.m3_result_sample_offsets(res), (batch + 1,)).copy()
             out.sample_offsets = off
@@ -232,6 +294,10 @@ class B200Session:
             out.pcm = out.audio = None
             if host_copy:
                 out.pcm = np.ctypeslib.as_array(self._lib.m3_result_pcm(res), (max(total, 1),))[:total]
+                nbytes = C.c_int64()
+                sp = self._lib.m3_result_stream(res, C.byref(nbytes))
+                if nbytes.value:
+                    out.stream = np.ctypeslib.as_array(sp, (nbytes.value,))
                 if keep_float:
                     out.audio = np.ctypeslib.as_array(self._lib.m3_result_audio(res), (max(total, 1),))[:total]
             out.device_ms = float(self._lib.m3_result_device_ms(res))
