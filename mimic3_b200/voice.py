@@ -6,7 +6,9 @@ line by line, :meth:`B200Voice.load_from_directory` reads the same voice directo
 (``voice.py:246-321``), and sessions are shared per ``generator.onnx`` path under a
 lock (``voice.py:71-72,277-299``).  The text front-ends (``text_to_phonemes`` --
 gruut / espeak-ng / epitran, ``voice.py:413-775``) are out of scope:
-ids are the engine's input.  The one addition is :meth:`ids_to_audio_batch`.
+phonemes or ids are the input.  Additions: :meth:`ids_to_audio_batch` (one setting for all rows) and
+:meth:`ids_to_audio_rows` (per-sentence settings + volume in ONE engine call, what the batched
+``end_utterance`` of ``mimic3_b200.tts`` uses).
 """
 from __future__ import annotations
 
@@ -22,10 +24,12 @@ from types import SimpleNamespace
 import numpy as np
 
 from .engine import B200Session
+from .phonemes import load_phoneme_ids, load_phoneme_map, phonemes2ids
 
 _LOGGER = logging.getLogger(__name__)
 
 DEFAULT_RATE = 1.0
+DEFAULT_VOLUME = 100.0   # mimic3_tts/const.py
 B200_PROVIDER = "B200ExecutionProvider"
 
 
@@ -48,6 +52,12 @@ class VoiceConfig:
         self.audio = _ns(audio)
         self.inference = _ns(inference)
         self.model = _ns(model)
+        # PhonemesConfig defaults, config.py:147-176
+        phonemes = {"pad": "_", "bos": None, "eos": None, "blank": "#", "blank_word": None, "blank_between": "words",
+                    "blank_at_start": True, "blank_at_end": True, "simple_punctuation": True, "punctuation_map": None,
+                    "separate": None, "separate_graphemes": False, "separate_tones": False, "tone_before": False,
+                    "phoneme_map": None, "auto_bos_eos": False, **(data.get("phonemes") or {})}
+        self.phonemes = SimpleNamespace(**phonemes)  # maps stay dicts
         self.datasets = [_ns(d) for d in data.get("datasets", [])]
         self.phonemizer = data.get("phonemizer")
         self.text_language = data.get("text_language")
@@ -61,31 +71,35 @@ class VoiceConfig:
         return VoiceConfig(json.loads(config_file.read()))
 
 
-def load_phoneme_ids(ids_file: typing.TextIO) -> typing.Dict[str, int]:
-    """``phonemes.txt``: one ``<id> <phoneme>`` per line (what ``phonemes2ids.load_phoneme_ids``
-    reads at ``voice.py:268-271``)."""
-    out: typing.Dict[str, int] = {}
-    for line in ids_file:
-        line = line.rstrip("\n")
-        if not line.strip() or line.startswith("#"):
-            continue
-        pid, _, phoneme = line.partition(" ")
-        out[phoneme] = int(pid)
-    return out
-
-
 class B200Voice:
     """Drop-in for the ids->audio half of ``Mimic3Voice`` backed by libm3b200."""
 
     _SHARED_MODELS: typing.Dict[str, B200Session] = {}
     _SHARED_MODELS_LOCK = threading.Lock()
 
-    def __init__(self, config, onnx_model, phoneme_to_id, phoneme_map=None, speaker_map=None):
+    def __init__(self, config, onnx_model, phoneme_to_id, phoneme_map=None, speaker_map=None,
+                 phonemes_to_ids_fn=None):
         self.config = config
         self.onnx_model = onnx_model
         self.phoneme_to_id = phoneme_to_id
         self.phoneme_map = phoneme_map
         self.speaker_map = speaker_map
+        # any callable with the phonemes2ids.phonemes2ids keyword signature (voice.py:133-152); default:
+        # the restatement in mimic3_b200.phonemes
+        self.phonemes_to_ids_fn = phonemes_to_ids_fn or phonemes2ids
+
+    # -- voice.py:126-152 ---------------------------------------------------------------
+    def phonemes_to_ids(self, phonemes) -> typing.List[int]:
+        """Convert phonemes to ids for a voice model (see phonemes.txt)."""
+        pc = self.config.phonemes
+        phoneme_map = self.phoneme_map or pc.phoneme_map
+        return self.phonemes_to_ids_fn(
+            word_phonemes=phonemes, phoneme_to_id=self.phoneme_to_id, pad=pc.pad, bos=pc.bos, eos=pc.eos,
+            auto_bos_eos=pc.auto_bos_eos, blank=pc.blank, blank_word=pc.blank_word, blank_between=pc.blank_between,
+            blank_at_start=pc.blank_at_start, blank_at_end=pc.blank_at_end, simple_punctuation=pc.simple_punctuation,
+            punctuation_map=pc.punctuation_map, separate=pc.separate, separate_graphemes=pc.separate_graphemes,
+            separate_tones=pc.separate_tones, tone_before=pc.tone_before, phoneme_map=phoneme_map,
+            fail_on_missing=False)
 
     # -- voice.py:89 ------------------------------------------------------------------
     def text_to_phonemes(self, text, text_language=None):
@@ -159,6 +173,33 @@ class B200Voice:
         _LOGGER.debug("RTF: %s", (end_time - start_time) / audio_sec if audio_sec > 0 else 0.0)
         return audios
 
+    def ids_to_audio_rows(self, batch_ids, speakers=None, length_scales=None, noise_scales=None, noise_ws=None,
+                          rates=None, volumes=None, seed: typing.Optional[int] = None,
+                          ) -> typing.List[np.ndarray]:
+        """One engine call for sentences that each carry their own settings (``Mimic3Settings`` of the
+        sentence: speaker / length_scale / noise_scale / noise_w / rate / volume, ``tts.py:519-543``).
+        ``volumes`` are the reference's 0-100 values; rows whose volume is not 100 go through the device
+        equivalent of ``audioop.mul(audio, 2, volume / 100)`` (``tts.py:540-543``).  ``out[i]`` is what
+        ``_speak_sentence_phonemes`` would hand to ``AudioResult`` for sentence i."""
+        n = len(batch_ids)
+        pick = lambda seq, i, default=None: default if seq is None else seq[i]
+        rows = np.stack([self._scales(pick(length_scales, i), pick(noise_scales, i), pick(noise_ws, i),
+                                      pick(rates, i, DEFAULT_RATE)) for i in range(n)]) if n else np.zeros((0, 3), np.float32)
+        lengths = np.array([len(p) for p in batch_ids], dtype=np.int64)
+        text = np.zeros((n, max(1, int(lengths.max()) if n else 1)), dtype=np.int64)
+        for i, p in enumerate(batch_ids):
+            text[i, : len(p)] = np.asarray(p, dtype=np.int64)
+        sid = None
+        if self.config.is_multispeaker and self.onnx_model.info.has_speaker_embedding:
+            sid = np.array([self._resolve_speaker(pick(speakers, i)) for i in range(n)], dtype=np.int64)
+        if seed is None:
+            seed = int(np.random.randint(0, 2 ** 31 - 1)) if (rows[:, 0].any() or rows[:, 2].any()) else 0
+        volume = None
+        if volumes is not None and any(v != DEFAULT_VOLUME for v in volumes):
+            volume = np.array([v / 100.0 for v in volumes], dtype=np.float64)
+        r = self.onnx_model.infer(text, lengths, None, sid, seed=seed, row_scales=rows.astype(np.float32), volume=volume)
+        return [r.utterance_pcm(b) for b in range(n)]
+
     # -- voice.py:245-376 ------------------------------------------------------------------------
     @staticmethod
     def load_from_directory(voice_dir, session_options=None, providers=None, share_models: bool = True,
@@ -187,12 +228,8 @@ class B200Voice:
         phoneme_map = None
         phoneme_map_path = voice_dir / "phoneme_map.txt"
         if phoneme_map_path.is_file():
-            phoneme_map = {}
             with open(phoneme_map_path, "r", encoding="utf-8") as map_file:
-                for line in map_file:
-                    parts = line.strip("\r\n").split(" ")
-                    if len(parts) >= 2 and parts[0]:
-                        phoneme_map[parts[0]] = parts[1:]
+                phoneme_map = load_phoneme_map(map_file)
         speaker_map = None
         speaker_map_path = voice_dir / "speaker_map.csv"
         if speaker_map_path.is_file():

@@ -114,3 +114,47 @@ def test_per_utterance_scales_equal_uniform_runs(built_library, voices):
     with pytest.raises(ValueError, match="row_scales"):
         sess.infer(ids, lens, None, sid, row_scales=np.array([[0, 1, 0]] * 2, dtype=np.float32))
     sess.close()
+
+
+@pytest.mark.gpu
+def test_batched_queue_equals_sentence_by_sentence(built_library, voices):
+    """all sentences of an utterance in one engine call == the reference's loop of one
+    `ids_to_audio` per sentence followed by the host post chain (tts.py:519-551), result by result; and the
+    device-assembled WAV == the HTTP server's host-side WAV assembly (mimic3_http/synthesis.py:60-85)."""
+    from mimic3_b200 import tts
+    from mimic3_b200.voice import B200Voice
+    voice = B200Voice.load_from_directory(voices("tiny_ms"))
+    settings = tts.B200Settings(voice="x/tiny", noise_scale=0.0, noise_w=0.0)
+
+    def fill(q):
+        q.speak_phonemes([["a", "b"], ["c"]])
+        q.add_break(40)
+        q.settings.speaker, q.settings.length_scale, q.settings.volume = "p201", 1.4, 35.0
+        q.speak_phonemes([["d"], ["e", "f", "g"]])
+        q.set_mark("m1")
+        q.settings.rate, q.settings.volume = 1.25, 100.0
+        q.speak_phonemes([["h", "a"]], is_utterance=False)
+        q.speak_phonemes([["b"]])
+        q.add_break(5)
+
+    q = tts.B200UtteranceQueue(tts.B200Settings(**vars(settings)), lambda key: voice)
+    fill(q)
+    plan = tts.plan_sentences(q._results)
+    end_settings = tts.B200Settings(**vars(q.settings))
+    got = list(q.end_utterance())
+    assert len(got) == len(plan)
+    n_sent = 0
+    for g, item in zip(got, plan):
+        if isinstance(item, tts._Sentence):   # the reference's per-sentence path on the same engine
+            n_sent += 1
+            s = item.settings or end_settings
+            audio = voice.ids_to_audio(voice.phonemes_to_ids(item.phonemes), speaker=s.speaker, length_scale=s.length_scale,
+                                       noise_scale=s.noise_scale, noise_w=s.noise_w, rate=s.rate)
+            want = audio if s.volume == 100.0 else pc.audioop_mul_int16(audio, s.volume / 100.0)
+            assert isinstance(g, tts.AudioResult) and g.audio_bytes == want.tobytes()
+        else:
+            assert g is item
+    assert n_sent == 3
+    q2 = tts.B200UtteranceQueue(tts.B200Settings(**vars(settings)), lambda key: voice)
+    fill(q2)
+    assert q2.end_utterance_wav() == tts.results_to_wav_bytes(got)

@@ -1,0 +1,175 @@
+"""CPU tests of the callers' side: sentence grouping of end_utterance against
+goldens produced by the reference's own code, the batched queue over a recording fake engine, phonemes->ids."""
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from mimic3_b200 import tts
+from mimic3_b200.phonemes import load_phoneme_ids, load_phoneme_map, phonemes2ids
+from mimic3_b200.voice import B200Voice, VoiceConfig
+
+GOLDEN = Path(__file__).resolve().parent / "golden" / "end_utterance_plans.json"
+
+
+def _settings(d):
+    return tts.B200Settings(voice=d["voice"], speaker=d["speaker"], length_scale=d["length_scale"],
+                            volume=d["volume"], rate=d["rate"])
+
+
+def test_plan_sentences_matches_reference_end_utterance():
+    """tests/golden/make_golden_end_utterance.py ran the unmodified mimic3_tts/tts.py:470-515 over 120 random
+    queues; plan_sentences must yield the same items, sentences and settings objects."""
+    cases = json.loads(GOLDEN.read_text())["cases"]
+    assert len(cases) >= 100
+    spoken = 0
+    for case in cases:
+        queue = []
+        for q in case["queue"]:
+            if q["kind"] == "phonemes":
+                queue.append(tts.B200Phonemes(current_settings=_settings(q["settings"]), phonemes=q["phonemes"],
+                                              is_utterance=q["is_utterance"]))
+            elif q["kind"] == "break":
+                queue.append(tts.AudioResult(sample_rate_hz=22050, audio_bytes=bytes(int(q["ms"] / 1000.0 * 22050) * 2)))
+            else:
+                queue.append(tts.MarkResult(name=q["name"]))
+        plan = tts.plan_sentences(queue)
+        assert len(plan) == len(case["yielded"])
+        for got, want in zip(plan, case["yielded"]):
+            if want["kind"] == "speak":
+                spoken += 1
+                assert isinstance(got, tts._Sentence) and got.phonemes == want["phonemes"]
+                assert (got.settings is None) == (want["settings"] is None)
+                if got.settings is not None:
+                    assert got.settings == _settings(want["settings"])
+            elif want["kind"] == "break":
+                assert isinstance(got, tts.AudioResult) and len(got.audio_bytes) == want["n_bytes"]
+            else:
+                assert isinstance(got, tts.MarkResult) and got.name == want["name"]
+    assert spoken > 200
+
+
+class FakeSession:
+    class info:
+        has_speaker_embedding = 1
+        hop_length = 4
+
+    def __init__(self):
+        self.calls = []
+
+    def infer(self, text, lengths, scales, sid, seed=0, **kw):
+        self.calls.append(dict(text=text.copy(), lengths=lengths.copy(), scales=scales, sid=None if sid is None else sid.copy(),
+                               seed=seed, **kw))
+        fake = self
+
+        class R:
+            def utterance_pcm(self_, b):  # length and content identify the row
+                return np.full(int(lengths[b]) * 4, int(text[b, 0]), dtype=np.int16)
+
+            def stream_bytes(self_):
+                return b"STREAM%d" % len(fake.calls)
+        return R()
+
+
+def _voice(sample_rate=22050):
+    cfg = VoiceConfig({"model": {"n_speakers": 3}, "audio": {"sample_rate": sample_rate},
+                       "inference": {"length_scale": 1.0, "noise_scale": 0.667, "noise_w": 0.8},
+                       "phonemes": {"blank": "#", "blank_between": "words", "bos": "^", "eos": "$", "auto_bos_eos": True}})
+    p2i = {"_": 0, "^": 1, "$": 2, "#": 3, "a": 4, "b": 5, "c": 6, ",": 7, ".": 8}
+    return B200Voice(cfg, FakeSession(), p2i, None, {"spk": 2})
+
+
+def test_queue_batches_one_call_per_voice_and_keeps_order():
+    voices = {"en/a": _voice(), "de/b": _voice(16000)}
+    q = tts.B200UtteranceQueue(tts.B200Settings(voice="en/a"), voices.__getitem__)
+    q.speak_phonemes([["a"], ["b"]])                      # sentence 0 (settings: queue default, None -> self.settings)
+    q.settings.length_scale, q.settings.volume = 1.5, 50.0
+    q.add_break(100)
+    q.speak_phonemes([["b", "c"]])                        # sentence 1: spoken with the PREVIOUS item's settings
+    q.voice = "de/b#spk"
+    q.set_mark("here")
+    q.speak_phonemes([["c"]], is_utterance=False)
+    q.speak_phonemes([["a"]])                             # joins the open sentence; settings changed -> see reference rule
+    out = list(q.end_utterance())
+    kinds = [type(r).__name__ for r in out]
+    assert kinds == ["AudioResult", "AudioResult", "AudioResult", "MarkResult", "AudioResult"]
+    assert len(out[1].audio_bytes) == 2 * 2205                                # the 100 ms break, untouched
+    a, b = voices["en/a"].onnx_model.calls, voices["de/b"].onnx_model.calls
+    assert len(a) == 1 and len(b) == 1                                        # one engine call per voice
+    # Reference rules (tts.py:470-515, 525): sentence 0 is spoken with settings=None -> the system's settings AT
+    # end_utterance time (voice de/b#spk, length 1.5, volume 50); sentence 1 with the settings of the item queued
+    # before it (en/a defaults); the last sentence with those of the non-utterance part before it (de/b).
+    ca, cb = a[0], b[0]
+    assert ca["text"].shape[0] == 1 and ca["scales"] is None
+    ids1 = voices["en/a"].phonemes_to_ids([["b", "c"]])
+    assert ca["text"][0, : len(ids1)].tolist() == ids1 and ca["lengths"][0] == len(ids1)
+    np.testing.assert_allclose(ca["row_scales"], [[0.667, 1.0, 0.8]], rtol=1e-6)
+    assert ca["volume"] is None and ca["sid"].tolist() == [0]
+    assert cb["text"].shape[0] == 2                                           # both de/b sentences in ONE call
+    ids0, ids2 = voices["de/b"].phonemes_to_ids([["a"], ["b"]]), voices["de/b"].phonemes_to_ids([["c"], ["a"]])
+    assert cb["text"][0, : len(ids0)].tolist() == ids0 and cb["text"][1, : len(ids2)].tolist() == ids2
+    np.testing.assert_allclose(cb["row_scales"], [[0.667, 1.5, 0.8]] * 2, rtol=1e-6)
+    np.testing.assert_allclose(cb["volume"], [0.5, 0.5])
+    assert cb["sid"].tolist() == [2, 2]
+    assert [r.sample_rate_hz for r in out if isinstance(r, tts.AudioResult)] == [16000, 22050, 22050, 16000]
+    assert len(out[0].audio_bytes) == 2 * 4 * len(ids0) and len(out[4].audio_bytes) == 2 * 4 * len(ids2)
+    assert not q._results
+    # byte-for-byte what results_to_wav_bytes of the reference's HTTP path would assemble
+    wav = tts.results_to_wav_bytes(out)
+    assert wav[:4] == b"RIFF" and len(wav) == 44 + sum(len(r.audio_bytes) for r in out if isinstance(r, tts.AudioResult))
+
+
+def test_end_utterance_wav_folds_breaks_into_silences():
+    v = _voice()
+    q = tts.B200UtteranceQueue(tts.B200Settings(voice="en/a", noise_scale=0.0, noise_w=0.0), lambda key: v)
+    q.add_break(10)
+    q.speak_phonemes([["a"]])
+    q.add_break(20)
+    q.set_mark("m")
+    q.add_break(30)
+    q.speak_phonemes([["b"]])
+    assert q.end_utterance_wav() == b"STREAM1"
+    c = v.onnx_model.calls[0]
+    assert c["wav_header"] is True and c["seed"] == 0
+    assert c["lead_silence"].tolist() == [220, 0] and c["trail_silence"].tolist() == [441 + 661, 0]
+    assert c["sid"].tolist() == [0, 0] and c["volume"] is None
+    # two voices -> host assembly like the reference
+    v2 = _voice()
+    q = tts.B200UtteranceQueue(tts.B200Settings(voice="x"), {"x": v, "y": v2}.__getitem__)
+    q.speak_phonemes([["a"]])
+    q.voice = "y"
+    q.speak_phonemes([["b"]])
+    q.speak_phonemes([["c"]])
+    wav = q.end_utterance_wav()
+    assert wav[:4] == b"RIFF" and wav[8:12] == b"WAVE"
+
+
+def test_phonemes2ids_documented_behaviour():
+    p2i = {"_": 0, "^": 1, "$": 2, "#": 3, "a": 4, "b": 5, "ˈ": 6, ",": 7, ".": 8, "1": 9, "ma": 10}
+    words = [["a", "b"], ["b"]]
+    assert phonemes2ids(words, p2i) == [4, 5, 5]
+    assert phonemes2ids(words, p2i, blank="#") == [3, 4, 5, 3, 5, 3]                                  # words
+    assert phonemes2ids(words, p2i, blank="#", blank_between="tokens") == [3, 4, 3, 5, 3, 5, 3]
+    assert phonemes2ids(words, p2i, blank="#", blank_at_start=False, blank_at_end=False) == [4, 5, 3, 5]
+    assert phonemes2ids(words, p2i, blank="#", bos="^", eos="$", auto_bos_eos=True) == [3, 1, 3, 4, 5, 3, 5, 3, 2, 3]
+    assert phonemes2ids([["a", "?"], [";"]], p2i, simple_punctuation=True) == [4, 8, 7]
+    assert phonemes2ids([["a", "?"]], p2i, simple_punctuation=False) == [4]                             # unknown dropped
+    assert phonemes2ids([["ˈa"]], p2i, separate={"ˈ"}) == [6, 4]
+    assert phonemes2ids([["ma1"]], p2i, separate_tones=True) == [10, 9]
+    assert phonemes2ids([["ma1"]], p2i, separate_tones=True, tone_before=True) == [9, 10]
+    assert phonemes2ids([["x"]], p2i, phoneme_map={"x": ["a", "b"]}) == [4, 5]
+    assert phonemes2ids([], p2i, blank="#") == [] and phonemes2ids([["zz"]], p2i, blank="#") == []
+    with pytest.raises(KeyError):
+        phonemes2ids([["zz"]], p2i, fail_on_missing=True)
+    assert load_phoneme_ids(["0 _\n", "# comment\n", "\n", "3 #\n", "4  \n"]) == {"_": 0, "#": 3, " ": 4}
+    assert load_phoneme_map(["x a b\n", "\n", "y c\n"]) == {"x": ["a", "b"], "y": ["c"]}
+
+
+def test_voice_phonemes_to_ids_uses_config_and_injected_function():
+    v = _voice()
+    assert v.phonemes_to_ids([["a"], ["b", "c"]]) == [3, 1, 3, 4, 3, 5, 6, 3, 2, 3]
+    seen = {}
+    v.phonemes_to_ids_fn = lambda **kw: seen.update(kw) or [42]
+    assert v.phonemes_to_ids([["a"]]) == [42]
+    assert seen["blank"] == "#" and seen["auto_bos_eos"] is True and seen["fail_on_missing"] is False  # voice.py:133-152
