@@ -112,6 +112,7 @@ struct TcConvParams {
   const int* seg_len = nullptr;
   int in_scale = 1, out_scale = 1, rows_extra = 0;
   int ups_u = 1, ups_pad = 0, ups_cout = 0;
+  int wide = 0;  // 256-bit global stores in the polyphase epilogue (set by the launcher: M3B200_WIDE_IO + alignment)
 };
 bool conv_tc_supported(int K, int NC, int taps, int dil);
 void launch_conv_tc(const TcConvParams& p, int fmt, int n_seg, int max_seg_len, cudaStream_t st);
@@ -133,7 +134,9 @@ struct RowGemmTcParams {
   const int* vmap = nullptr;      // virtual row -> physical row, -1 for the zero row after each utterance
   const int4* rowinfo = nullptr;  // physical row -> (lo, hi, seg, 0)
   int vrows = 0;
+  int wide = 0;  // 256-bit global loads / stores (set by the launcher: M3B200_WIDE_IO + alignment)
 };
+bool wide_io_enabled();  // M3B200_WIDE_IO (read per launch)
 bool rowgemm_tc_supported(int K, int taps);
 int rowgemm_tc_nc(int N, int taps);
 size_t rowgemm_tc_weight_elems(int K, int N, int taps, int nc);

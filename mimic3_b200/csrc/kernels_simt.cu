@@ -31,6 +31,11 @@ void post_launch(const char* what, cudaStream_t st) {
     throw std::runtime_error(buf);
   }
 }
+bool wide_io_enabled() {
+  const char* e = getenv("M3B200_WIDE_IO");
+  return e && *e && *e != '0';
+}
+
 void ensure_max_dynamic_smem(const void* func) {
   static std::mutex mu;
   static std::set<const void*> done;

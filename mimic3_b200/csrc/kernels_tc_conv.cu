@@ -213,6 +213,23 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(TcConvParams p, 
             tc::tmem_ld_wait();
             if (!row_ok) continue;
             const int n0 = c * NC + j0;
+            if (p.epi == TC_UPS && p.wide) {
+              // same mapping, one full 32-byte sector per lane and store (Cout % 8 == 0: the 8 columns of a
+              // group share their phase)
+#pragma unroll
+              for (int e = 0; e < 16; e += 8) {
+                const int n = n0 + e;
+                if (n >= p.N) break;
+                const int phase = n / p.ups_cout, co = n - phase * p.ups_cout;
+                const int po = t * p.ups_u + phase - p.ups_pad;
+                if (po < 0 || po >= out_len) continue;
+                float o[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) o[k] = v[e + k] + p.bias[co + k];
+                tc::stg256(p.out + (out_base + po) * p.out_stride + co, o);
+              }
+              continue;
+            }
             if (p.epi == TC_UPS) {
               // column n = phase * Cout + co ; output row = t*u + phase - pad
 #pragma unroll 1
@@ -283,7 +300,12 @@ bool conv_tc_supported(int K, int NC, int taps, int dil) {
   return a_bytes + 2 * stage <= size_t(CT_SMEM_MAX);
 }
 
-void launch_conv_tc(const TcConvParams& p, int fmt, int n_seg, int max_seg_len, cudaStream_t st) {
+void launch_conv_tc(const TcConvParams& p_in, int fmt, int n_seg, int max_seg_len, cudaStream_t st) {
+  TcConvParams p = p_in;
+  p.wide = (p.epi == TC_UPS && wide_io_enabled() && p.ups_cout % 8 == 0 && p.out_stride % 8 == 0 &&
+            (reinterpret_cast<uintptr_t>(p.out) & 31u) == 0)
+               ? 1
+               : 0;
   const int rows = max_seg_len * p.in_scale + p.rows_extra;
   if (rows <= 0 || n_seg <= 0) return;
   const int rows_a = (CT_R + (p.taps - 1) * p.dil) | 1;  // odd row pitch: conflict-free chunk-major smem stores

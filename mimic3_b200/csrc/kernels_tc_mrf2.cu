@@ -52,18 +52,8 @@ __host__ __device__ inline WGeo make_wgeo(const MrfParams& p, int nslot) {
   return g;
 }
 __device__ __forceinline__ float wlrelu(float v, float s) { return fmaxf(v, s * v); }
-// 256-bit global accesses: one full 32-byte sector per lane and instruction (the row-per-lane pattern of the
-// epilogue warps touches 32 different lines per instruction; L1 handles one line per cycle)
-__device__ __forceinline__ void ldg256(const float* p, float* v) {
-  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
-               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
-               : "l"(p));
-}
-__device__ __forceinline__ void stg256(float* p, const float* v) {
-  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};\n" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
-               "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
-               : "memory");
-}
+using tc::ldg256;
+using tc::stg256;
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p)); }
 // chain order of a window: rotated by the window index, so that the SMs (which work on different windows at
 // any moment) do not all pull the same weight block from the same L2 slices at the same time; a function of

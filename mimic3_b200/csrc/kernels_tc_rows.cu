@@ -100,8 +100,15 @@ __global__ void __launch_bounds__(RG_THREADS, 4) rowgemm_tc_kernel(RowGemmTcPara
         if (physr[u] >= 0) {
           const int c8 = dsto[u] / RA;
           const float* src = p.in + (long long)physr[u] * p.in_stride + kb * RG_KB + c8 * 8;
-          la[u] = *reinterpret_cast<const float4*>(src);
-          lb[u] = *reinterpret_cast<const float4*>(src + 4);
+          if (p.wide) {  // one 32-byte sector per lane and instruction
+            float t8[8];
+            tc::ldg256(src, t8);
+            la[u] = make_float4(t8[0], t8[1], t8[2], t8[3]);
+            lb[u] = make_float4(t8[4], t8[5], t8[6], t8[7]);
+          } else {
+            la[u] = *reinterpret_cast<const float4*>(src);
+            lb[u] = *reinterpret_cast<const float4*>(src + 4);
+          }
         }
       }
       tc::mbar_wait(&empty_bar[s], (((kb / RG_STAGES) & 1) ^ 1));
@@ -153,7 +160,10 @@ __global__ void __launch_bounds__(RG_THREADS, 4) rowgemm_tc_kernel(RowGemmTcPara
         if (p.act == 1) v = fmaxf(v, 0.f);
         val[e] = v;
       }
-      if (n0 + 16 <= p.N && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {  // 4 x 128-bit stores per row
+      if (p.wide && n0 + 16 <= p.N && (reinterpret_cast<uintptr_t>(dst) & 31u) == 0) {  // 2 x 256-bit stores per row
+        tc::stg256(dst, val);
+        tc::stg256(dst + 8, val + 8);
+      } else if (n0 + 16 <= p.N && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {  // 4 x 128-bit stores per row
 #pragma unroll
         for (int e = 0; e < 16; e += 4) *reinterpret_cast<float4*>(dst + e) = make_float4(val[e], val[e + 1], val[e + 2], val[e + 3]);
       } else {
@@ -233,8 +243,10 @@ static void launch_rowgemm_inst(const RowGemmTcParams& p, size_t stage_bytes, cu
   rowgemm_tc_kernel<NC, ST><<<grid, RG_THREADS, ST * stage_bytes, st>>>(p);
 }
 
-void launch_rowgemm_tc(const RowGemmTcParams& p, cudaStream_t st) {
+void launch_rowgemm_tc(const RowGemmTcParams& p_in, cudaStream_t st) {
+  RowGemmTcParams p = p_in;
   if (p.vrows <= 0) return;
+  p.wide = (wide_io_enabled() && p.in_stride % 8 == 0 && (reinterpret_cast<uintptr_t>(p.in) & 31u) == 0) ? 1 : 0;
   if (p.nc != 64 && p.nc != 128) throw std::runtime_error("rowgemm_tc: unsupported column chunk");
   const int RA = (128 + p.taps - 1) | 1;
   const size_t a_pad = (size_t(2) * (RG_KB / 8) * RA * 16 + 127) & ~size_t(127);

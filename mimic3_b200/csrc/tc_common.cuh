@@ -218,5 +218,18 @@ struct Elem<0> {  // fp16
   }
 };
 
+// 256-bit global accesses: one full 32-byte sector per lane and instruction (the row-per-lane pattern of the
+// epilogue warps touches 32 different lines per instruction; L1 handles one line per cycle)
+__device__ __forceinline__ void ldg256(const float* p, float* v) {
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void stg256(float* p, const float* v) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};\n" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+               "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+               : "memory");
+}
+
 }  // namespace tc
 }  // namespace m3
