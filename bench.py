@@ -343,10 +343,10 @@ def main():
         dec_ms = stage_ms.get("dec_last", 0.0) / args.steps
         mrf_ms = stage_ms["mrf"] / args.steps
         if dec_ms > 0:   # dominant kernel: the fused last generator stage (upsample + MRF + conv_post)
-            k_name = "dec_last_kernel (ConvTranspose + MRF + conv_post, last stage)"
+            k_name = "dec_fused_kernel (ConvTranspose + MRF + conv_post, last generator stage)"
             k_flops = (fl["ups_stage"][-1] + fl["mrf_stage"][-1] + fl["post"]) * frames_ps
             k_ms = dec_ms
-            traffic = 393.1e6 * (GB / 64.0) / world  # ncu --set full capture at batch 64 (profiles/r01_ncu_final_tc_kernels.md), scaled
+            traffic = 397.0e6 * (GB / 64.0) / world  # dram read+write of one launch, ncu --set full at batch 64 (profiles/r01b_ncu_full_ws_kernels.md), scaled to this batch
         else:
             k_name, k_flops, k_ms, traffic = "MRF stages (mrf_tc_kernel x3)", fl["mrf"] * frames_ps, mrf_ms, None
         achieved_tf = k_flops / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
