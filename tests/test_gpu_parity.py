@@ -414,15 +414,15 @@ def test_rowgemm_variants_keep_text_side_results(voices, built_library, monkeypa
 
 
 def test_wide_io_is_bit_identical(sessions, monkeypatch):
-    """M3B200_WIDE_IO=1 (256-bit global loads/stores in the row GEMM and the polyphase upsampler epilogue) only
-    changes the width of memory instructions: every output bit must stay the same."""
+    """256-bit global loads/stores in the row GEMM and the polyphase upsampler epilogue (default) against the 128-bit
+    variant (M3B200_WIDE_IO=0): only the width of memory instructions changes, every output bit must stay the same."""
     rng = np.random.default_rng(123)
     sess = sessions("low_ms")
     ids, lens = _batch(rng, 50, [80, 3, 41, 1, 64, 17])
     sid = np.array([0, 5, 108, 7, 33, 2])
     for scales, seed in (((0.0, 1.0, 0.0), 0), ((0.667, 1.1, 0.8), 4)):
         ref = sess.infer(ids, lens, scales, sid, seed=seed, keep_float=True, debug_tensors=("x", "logw", "z"))
-        monkeypatch.setenv("M3B200_WIDE_IO", "1")
+        monkeypatch.setenv("M3B200_WIDE_IO", "0")
         alt = sess.infer(ids, lens, scales, sid, seed=seed, keep_float=True, debug_tensors=("x", "logw", "z"))
         monkeypatch.delenv("M3B200_WIDE_IO")
         for n in ("x", "logw", "z"):
@@ -433,7 +433,7 @@ def test_wide_io_is_bit_identical(sessions, monkeypatch):
     tiny = sessions("tiny_ms")
     ids, lens = _batch(rng, 20, [9, 30])
     ref = tiny.infer(ids, lens, (0.0, 1.0, 0.0), np.array([0, 1]), keep_float=True)
-    monkeypatch.setenv("M3B200_WIDE_IO", "1")
+    monkeypatch.setenv("M3B200_WIDE_IO", "0")
     alt = tiny.infer(ids, lens, (0.0, 1.0, 0.0), np.array([0, 1]), keep_float=True)
     monkeypatch.delenv("M3B200_WIDE_IO")
     np.testing.assert_array_equal(alt.audio, ref.audio)
