@@ -1491,7 +1491,8 @@ Result* run_inference(Voice& v, const int64_t* ids, const int64_t* lengths, int 
       p.ups_u = u.u;
       p.ups_pad = u.pad;
       p.ups_cout = u.cout;
-      launch_conv_tc(p, dv.tc_fmt, batch, Fmax, st);
+      if (ups_tc_enabled() && ups_tc_supported(p)) launch_ups_tc(p, dv.tc_fmt, batch, Fmax, st);  // opt-in, round-2 staging
+      else launch_conv_tc(p, dv.tc_fmt, batch, Fmax, st);
     } else {
       ConvParams p;
       p.in = cur;

@@ -116,6 +116,11 @@ struct TcConvParams {
 };
 bool conv_tc_supported(int K, int NC, int taps, int dil);
 void launch_conv_tc(const TcConvParams& p, int fmt, int n_seg, int max_seg_len, cudaStream_t st);
+// Staged for round 2 (kernels_tc_ups.cu): the TC_UPS case with a shared-memory bias and an early accumulator
+// release; selected by M3B200_UPS_V2=1 only -- not yet verified on hardware.
+bool ups_tc_enabled();
+bool ups_tc_supported(const TcConvParams& p);
+void launch_ups_tc(const TcConvParams& p, int fmt, int n_seg, int max_seg_len, cudaStream_t st);
 
 // Token-level conv-as-GEMM on tensor cores with fp16 hi/lo split operands (kernels_tc_rows.cu).
 // Weights: [chunk(nc cols)][K block(32)][tap][hi|lo][4][nc][8], 16-bit; nc = rowgemm_tc_nc(N, taps).

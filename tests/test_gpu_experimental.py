@@ -1,0 +1,34 @@
+"""Kernels staged for round 2: written and compiled in round 1, NOT yet run on hardware, never selected by
+default.  This file is skipped unless M3B200_TEST_EXPERIMENTAL=1, so the regular `-m gpu` run does not depend on
+them; the first GPU call of round 2 runs it to decide whether they graduate."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("M3B200_TEST_EXPERIMENTAL") != "1",
+                                 reason="round-2 staging kernels: set M3B200_TEST_EXPERIMENTAL=1")]
+
+
+def test_upsampler_v2_is_bit_identical(built_library, voices, monkeypatch):
+    """ups_tc_kernel (kernels_tc_ups.cu: bias in shared memory, early accumulator release) computes exactly what
+    conv_tc_kernel's TC_UPS epilogue computes: same MMAs, same `acc + bias` per output."""
+    from mimic3_b200.engine import B200Session
+    rng = np.random.default_rng(2)
+    for voice, nsym, lens_list in (("low_ms", 50, [80, 3, 41, 1, 64, 17, 100]), ("tiny_ms", 20, [9, 30, 1])):
+        sess = B200Session(str(voices(voice)))
+        T = max(lens_list)
+        ids = np.zeros((len(lens_list), T), dtype=np.int64)
+        for b, L in enumerate(lens_list):
+            ids[b, :L] = rng.integers(4, nsym, size=L)
+        lens = np.array(lens_list, dtype=np.int64)
+        sid = rng.integers(0, sess.info.n_speakers, size=len(lens_list))
+        ref = sess.infer(ids, lens, (0.667, 1.0, 0.8), sid, seed=3, keep_float=True)
+        monkeypatch.setenv("M3B200_UPS_V2", "1")
+        alt = sess.infer(ids, lens, (0.667, 1.0, 0.8), sid, seed=3, keep_float=True)
+        monkeypatch.delenv("M3B200_UPS_V2")
+        np.testing.assert_array_equal(alt.frames, ref.frames)
+        np.testing.assert_array_equal(alt.audio, ref.audio)
+        np.testing.assert_array_equal(alt.pcm, ref.pcm)
+        sess.close()
