@@ -388,7 +388,6 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
 
-constexpr int LN_MAXC = 1024;
 
 __device__ __forceinline__ void warp_layernorm(float* v, int nper, int C, int lane, const float* gamma,
                                                const float* beta, int act) {

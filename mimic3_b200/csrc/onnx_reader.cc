@@ -27,10 +27,10 @@ uint64_t varint(Span& s) {
 }
 
 struct Field {
-  uint32_t number;
-  uint32_t wire;
-  uint64_t value;  // wire 0 / 1 / 5
-  Span bytes;      // wire 2
+  uint32_t number = 0;
+  uint32_t wire = 0;
+  uint64_t value = 0;          // wire 0 / 1 / 5
+  Span bytes{nullptr, nullptr};  // wire 2
 };
 
 bool next(Span& s, Field& f) {
