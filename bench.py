@@ -6,9 +6,12 @@
 
 Workload = BASELINE.json configs[2] (the one the metric is quoted on): an en_US/vctk_low-shaped
 voice (109 speakers, synthetic random weights -- no real voice is reachable offline), batch 256,
-80 ids per utterance, sid[b] = b mod 109, PCG64(1234); the batch is sharded by rows over the
-N ranks (strong scaling, no collective on the compute path).  A "step" = one pass of the hot
-path over the whole batch.  Prints ONE JSON line on rank 0.
+80 ids per utterance, sid[b] = b mod 109, PCG64(1234).  Utterances are independent, so every rank
+runs this workload on its own rows with no collective on the compute path: by default per-GPU
+work is fixed (weak scaling, global batch 256 x N, as the bench contract prescribes for a path
+that partitions); ``--scaling strong`` shards ONE batch of 256 over the N ranks instead
+(BASELINE configs[2] literally: 32 utterances per GPU at N = 8).  A "step" = one pass of the hot
+path over the whole (global) batch.  Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
 
@@ -163,7 +166,7 @@ def run_reference(args, rank: int, world: int):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "configs[2]: vctk_low-shaped synthetic voice, 109 speakers, batch=256 x 80 ids",
                    "sample": f"{sample} utterances of the batch per step, batch-1 loop"},
         "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port",
@@ -184,7 +187,9 @@ def main():
     ap.add_argument("--cpu-baseline-utts", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--deterministic", action="store_true", help="noise scales 0 (parity settings)")
-    ap.add_argument("--batch", type=int, default=GLOBAL_BATCH, help="global batch override (profiling runs only)")
+    ap.add_argument("--batch", type=int, default=GLOBAL_BATCH, help="batch override (profiling runs only)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --batch utterances PER GPU (default); strong: --batch utterances sharded over all GPUs")
     ap.add_argument("--profile-only", action="store_true", help="skip stage/e2e/cpu passes (ncu runs)")
     args = ap.parse_args()
 
@@ -221,7 +226,7 @@ def main():
     scales = (0.0, 1.0, 0.0) if args.deterministic else (sess.info.noise_scale, sess.info.length_scale, sess.info.noise_w)
 
     # -- inputs: rank r owns rows [r*B/N, (r+1)*B/N) ------------------------------------------
-    GB = args.batch
+    GB = args.batch * world if args.scaling == "weak" else args.batch  # global batch of one step
     ids, lengths, sid = make_inputs(GB)
     per = GB // world
     lo, hi = rank * per, (rank + 1) * per if rank < world - 1 else GB
@@ -354,11 +359,13 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": wall_max / args.steps * 1e3, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None,
+            "scaling": args.scaling, "vs_baseline": None,
             "dtype": "fp16 tensor-core operands + fp32 accumulate/residual (flow, decoder); f32 (text encoder, durations)",
             "data": "synthetic",
             "config": {"workload": "configs[2]: vctk_low-shaped synthetic voice (109 speakers, random weights), "
-                                   "global batch 256 x 80 ids, sid=b%109, rows sharded over ranks",
+                                   + (f"{args.batch} x 80 ids per GPU (weak scaling: global batch {GB}), sid=b%109"
+                                      if args.scaling == "weak" else
+                                      f"one batch of {GB} x 80 ids sharded by rows over the ranks (strong scaling), sid=b%109"),
                        "global_batch": GB, "ids_per_utterance": IDS_PER_UTT,
                        "scales": [float(s) for s in scales], "parallelism": f"batch-shard x{world}",
                        "frames_per_step": tot_frames / args.steps, "samples_per_step": tot_samples / args.steps,
