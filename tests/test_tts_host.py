@@ -64,6 +64,8 @@ class FakeSession:
         fake = self
 
         class R:
+            total_samples = int(lengths.sum()) * 4
+
             def utterance_pcm(self_, b):  # length and content identify the row
                 return np.full(int(lengths[b]) * 4, int(text[b, 0]), dtype=np.int16)
 
@@ -173,3 +175,27 @@ def test_voice_phonemes_to_ids_uses_config_and_injected_function():
     v.phonemes_to_ids_fn = lambda **kw: seen.update(kw) or [42]
     assert v.phonemes_to_ids([["a"]]) == [42]
     assert seen["blank"] == "#" and seen["auto_bos_eos"] is True and seen["fail_on_missing"] is False  # voice.py:133-152
+
+
+def test_ids_to_audio_inputs_match_reference_goldens():
+    """tests/golden/make_golden_ids_to_audio.py called the unmodified Mimic3Voice.ids_to_audio (voice.py:154-243) with a
+    recording fake in place of the ORT session over 192 argument combinations; B200Voice must hand the engine the
+    same `input`, `input_lengths`, `scales` and `sid` (names map to m3_infer's arguments, voice.py:180-218)."""
+    g = json.loads((GOLDEN.parent / "ids_to_audio_inputs.json").read_text())
+    assert len(g["cases"]) >= 150
+    for c in g["cases"]:
+        cfg = VoiceConfig({"model": {"n_speakers": 3 if c["multispeaker"] else 1}, "inference": g["defaults"]})
+        assert cfg.is_multispeaker == c["multispeaker"]
+        v = B200Voice(cfg, FakeSession(), {}, None, c["speaker_map"])
+        v.ids_to_audio(c["ids"], speaker=c["speaker"], length_scale=c["length_scale"], noise_scale=c["noise_scale"],
+                       noise_w=c["noise_w"], rate=c["rate"])
+        call, want = v.onnx_model.calls[-1], c["inputs"]
+        assert call["text"].dtype == np.int64 and list(call["text"].shape) == want["input"]["shape"]
+        assert call["text"].reshape(-1).tolist() == want["input"]["values"]
+        assert call["lengths"].dtype == np.int64 and call["lengths"].tolist() == want["input_lengths"]["values"]
+        assert call["scales"].dtype == np.float32 and want["scales"]["dtype"] == "float32"
+        np.testing.assert_array_equal(call["scales"], np.array(want["scales"]["values"], dtype=np.float32))
+        if "sid" in want:
+            assert call["sid"].dtype == np.int64 and call["sid"].tolist() == want["sid"]["values"]
+        else:
+            assert call["sid"] is None
