@@ -199,3 +199,68 @@ def test_ids_to_audio_inputs_match_reference_goldens():
             assert call["sid"].dtype == np.int64 and call["sid"].tolist() == want["sid"]["values"]
         else:
             assert call["sid"] is None
+
+
+def test_queue_results_match_reference_speak_sentence_goldens():
+    """tests/golden/make_golden_speak_sentence.py ran the reference's end_utterance AND _speak_sentence_phonemes
+    (tts.py:470-551) over 80 random queues with fake voices whose output depends on every argument they receive.
+    The batched queue, given the same fakes behind `ids_to_audio_rows`, must yield byte-identical AudioResults:
+    same voice, ids, speaker, scales, rate, and the reference's audioop.mul volume step."""
+    import hashlib
+    import sys
+    sys.path.insert(0, str(GOLDEN.parent))
+    from fakes import fake_audio, fake_ids, sample_rate_of
+    from oracle.post_chain import audioop_mul_int16
+
+    class FakeBatchVoice:
+        def __init__(self, key, log):
+            from types import SimpleNamespace
+            self.key, self.log = key, log
+            self.config = SimpleNamespace(audio=SimpleNamespace(sample_rate=sample_rate_of(key)))
+
+        def phonemes_to_ids(self, phonemes):
+            return fake_ids(phonemes)
+
+        def ids_to_audio_rows(self, batch_ids, speakers=None, length_scales=None, noise_scales=None, noise_ws=None,
+                              rates=None, volumes=None, seed=None):
+            self.log.append(len(batch_ids))
+            out = []
+            for i, ids in enumerate(batch_ids):
+                a = fake_audio(self.key, ids, speakers[i], length_scales[i], noise_scales[i], noise_ws[i], rates[i])
+                out.append(a if volumes[i] == 100.0 else audioop_mul_int16(a, volumes[i] / 100.0))  # device post chain
+            return out
+
+    cases = json.loads((GOLDEN.parent / "speak_sentence_results.json").read_text())["cases"]
+    n_audio = n_calls = 0
+    for case in cases:
+        log, voices = [], {}
+        q = tts.B200UtteranceQueue(tts.B200Settings(voice="v0"), lambda key: voices.setdefault(key, FakeBatchVoice(key, log)))
+        for item in case["queue"]:
+            if item["kind"] == "phonemes":
+                s = item["settings"]
+                q._results.append(tts.B200Phonemes(
+                    current_settings=tts.B200Settings(voice=s["voice"], speaker=s["speaker"], length_scale=s["length_scale"],
+                                                      noise_scale=s["noise_scale"], noise_w=s["noise_w"], volume=s["volume"],
+                                                      rate=s["rate"]),
+                    phonemes=item["phonemes"], is_utterance=item["is_utterance"]))
+            elif item["kind"] == "break":
+                q.add_break(item["ms"])
+            else:
+                q.set_mark(item["name"])
+        e = case["end_settings"]
+        q.settings = tts.B200Settings(voice=e["voice"], speaker=e["speaker"], length_scale=e["length_scale"],
+                                      noise_scale=e["noise_scale"], noise_w=e["noise_w"], volume=e["volume"], rate=e["rate"])
+        got = list(q.end_utterance())
+        assert len(got) == len(case["yielded"])
+        for g, want in zip(got, case["yielded"]):
+            if want["kind"] == "audio":
+                n_audio += 1
+                assert isinstance(g, tts.AudioResult) and g.sample_rate_hz == want["sample_rate"]
+                assert len(g.audio_bytes) == want["n_bytes"]
+                assert hashlib.sha256(g.audio_bytes).hexdigest() == want["sha256"]
+            else:
+                assert isinstance(g, tts.MarkResult) and g.name == want["name"]
+        assert sum(log) == len(case["calls"])                    # same sentences synthesised ...
+        assert len(log) == len({c["voice"] for c in case["calls"]})   # ... in ONE engine call per voice
+        n_calls += len(log)
+    assert n_audio > 250 and n_calls < 231
