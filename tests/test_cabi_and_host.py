@@ -124,3 +124,19 @@ def test_voice_directory_files(voices):
     cfg = VoiceConfig.load(open(d / "config.json"))
     assert cfg.is_multispeaker and cfg.audio.sample_rate == 22050
     assert cfg.inference.noise_w == pytest.approx(0.8)
+
+
+def test_entry_points_reject_null_arguments_without_a_gpu(built_library):
+    """Argument errors are reported, never dereferenced: no GPU needed to see that."""
+    lib = engine.load_library()
+    res = ctypes.c_void_p()
+    assert lib.m3_infer_ex(None, None, None, 1, 1, None, None, None, ctypes.byref(res)) == engine.M3_ERR_INVALID
+    assert b"NULL" in lib.m3_last_error()
+    assert lib.m3_infer(None, None, None, 1, 1, None, None, 0, 0, ctypes.byref(res)) == engine.M3_ERR_INVALID
+    n = ctypes.c_int64(-1)
+    assert not lib.m3_result_stream(None, ctypes.byref(n)) and n.value == 0
+    assert lib.m3_result_batch(None) == 0 and lib.m3_result_kernel_launches(None) == 0
+    lib.m3_result_free(None)
+    lib.m3_voice_free(None)
+    assert ctypes.sizeof(engine.InferOpts) == 56          # layout of m3_infer_opts (include/m3b200.h)
+    assert engine.InferOpts.row_scales.offset == 16 and engine.InferOpts.wav_header.offset == 48
