@@ -140,3 +140,36 @@ def test_entry_points_reject_null_arguments_without_a_gpu(built_library):
     lib.m3_voice_free(None)
     assert ctypes.sizeof(engine.InferOpts) == 56          # layout of m3_infer_opts (include/m3b200.h)
     assert engine.InferOpts.row_scales.offset == 16 and engine.InferOpts.wav_header.offset == 48
+
+
+def test_header_is_plain_c_and_links(built_library, tmp_path):
+    """include/m3b200.h must be consumable from C (the reference-side binding is ctypes / cgo-style FFI): compile a
+    C99 translation unit against it, link the shared library, call the GPU-free entry points."""
+    import shutil
+    import subprocess
+    if not shutil.which("gcc"):
+        pytest.skip("gcc not available")
+    src = tmp_path / "abi.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "m3b200.h"
+_Static_assert(sizeof(m3_infer_opts) == 56, "m3_infer_opts layout");
+_Static_assert(sizeof(m3_voice_info) == 64, "m3_voice_info layout");
+int main(void) {
+  unsigned char h[44];
+  m3_voice* v = 0;
+  if (m3_wav_header(22050, 1000, h) != M3_OK || memcmp(h, "RIFF", 4) != 0) return 1;
+  if (m3_voice_load("/nonexistent/voice", 0, &v) == M3_OK || v != 0) return 2;
+  if (strlen(m3_last_error()) == 0) return 3;
+  printf("%s|%d\n", m3_version(), (int)m3_device_count());
+  return 0;
+}
+''')
+    exe = tmp_path / "abi"
+    lib = Path(built_library)
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", str(ROOT / "include"), str(src), "-o", str(exe),
+                    str(lib), f"-Wl,-rpath,{lib.parent}"], check=True, capture_output=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, out
+    assert "sm_100a" in out.stdout
