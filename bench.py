@@ -387,7 +387,11 @@ def main():
             "clocks": clocks,
         }
         if not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(vd, ids, sid, scales, args.cpu_baseline_utts)
+            try:
+                line["cpu_baseline"] = cpu_baseline(vd, ids, sid, scales, args.cpu_baseline_utts)
+            except Exception as e:  # the CPU leg must never cost the GPU line
+                line["cpu_baseline"] = {"value": None, "unit": "samples/s", "cores": 0, "kind": "port",
+                                        "sample": f"failed: {e!r}"}
         print(json.dumps(line), flush=True)
     if distributed:
         dist.barrier()
