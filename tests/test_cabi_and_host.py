@@ -173,3 +173,17 @@ int main(void) {
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 0, out
     assert "sm_100a" in out.stdout
+
+
+def test_loader_survives_corrupted_voice_files(built_library):
+    """ORT raises on a bad model; the native loader must do the same (error code -> exception), never crash the
+    server process (SURVEY.md §8b "Errors").  300 corrupted generator.onnx + 75 corrupted config.json variants."""
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, str(ROOT / "tests" / "fuzz_loader.py"), "7", "300"], capture_output=True,
+                         text=True, timeout=600)
+    assert out.returncode == 0, (out.returncode, out.stderr[-2000:])
+    assert "return codes:" in out.stdout
+    codes = eval(out.stdout.split("return codes:")[1].strip())
+    assert set(codes) <= {engine.M3_ERR_MODEL, engine.M3_ERR_IO, engine.M3_ERR_NOGPU, engine.M3_OK}, codes
+    assert codes.get(engine.M3_ERR_MODEL, 0) > 100
