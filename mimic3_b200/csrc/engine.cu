@@ -845,7 +845,8 @@ struct Run {
       q.vmap = vmap;
       q.rowinfo = rowinfo;
       q.vrows = vrows;
-      launch_rowgemm_tc(q, st);
+      if (rowgemm2_enabled() && rowgemm2_supported(q)) launch_rowgemm2(q, st);  // opt-in, round-2 staging
+      else launch_rowgemm_tc(q, st);
       return;
     }
     RowConvParams p;

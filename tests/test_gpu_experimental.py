@@ -32,3 +32,29 @@ def test_upsampler_v2_is_bit_identical(built_library, voices, monkeypatch):
         np.testing.assert_array_equal(alt.audio, ref.audio)
         np.testing.assert_array_equal(alt.pcm, ref.pcm)
         sess.close()
+
+
+def test_rowgemm_v2_is_bit_identical(built_library, voices, monkeypatch):
+    """rowgemm2_kernel (kernels_tc_rows2.cu: resident A, chunk loop, double-buffered accumulators) runs the same
+    MMAs in the same order per accumulator on the same packed weights as rowgemm_tc_kernel: the text side (encoder
+    output, projected statistics, log-durations, durations) and the audio must not move by a bit."""
+    from mimic3_b200.engine import B200Session
+    rng = np.random.Generator(np.random.PCG64(6))
+    names = ("x", "stats", "logw", "durations")
+    for voice, nsym, nspk, lens_list in (("low_ms", 50, 109, [80] * 20 + [11, 1, 64, 3]), ("tiny_ms", 20, 3, [40, 1, 17, 33])):
+        sess = B200Session(str(voices(voice)))
+        T = max(lens_list)
+        ids = np.zeros((len(lens_list), T), dtype=np.int64)
+        for b, L in enumerate(lens_list):
+            ids[b, :L] = rng.integers(4, nsym, size=L)
+        lens = np.array(lens_list, dtype=np.int64)
+        sid = (np.arange(len(lens_list)) % nspk).astype(np.int64)
+        ref = sess.infer(ids, lens, (0.667, 1.0, 0.8), sid, seed=5, debug_tensors=names)
+        monkeypatch.setenv("M3B200_ROWGEMM_V2", "1")
+        alt = sess.infer(ids, lens, (0.667, 1.0, 0.8), sid, seed=5, debug_tensors=names)
+        monkeypatch.delenv("M3B200_ROWGEMM_V2")
+        assert alt.launches == ref.launches
+        for n in names:
+            np.testing.assert_array_equal(alt.tensors[n], ref.tensors[n], err_msg=f"{voice}: {n}")
+        np.testing.assert_array_equal(alt.pcm, ref.pcm)
+        sess.close()
