@@ -845,8 +845,7 @@ struct Run {
       q.vmap = vmap;
       q.rowinfo = rowinfo;
       q.vrows = vrows;
-      if (rowgemm2_enabled() && rowgemm2_supported(q)) launch_rowgemm2(q, st);  // opt-in, round-2 staging
-      else launch_rowgemm_tc(q, st);
+      launch_rowgemm_tc(q, st);
       return;
     }
     RowConvParams p;
@@ -1492,7 +1491,7 @@ Result* run_inference(Voice& v, const int64_t* ids, const int64_t* lengths, int 
       p.ups_u = u.u;
       p.ups_pad = u.pad;
       p.ups_cout = u.cout;
-      if (ups_tc_enabled() && ups_tc_supported(p)) launch_ups_tc(p, dv.tc_fmt, batch, Fmax, st);  // opt-in, round-2 staging
+      if (ups_tc_enabled() && ups_tc_supported(p)) launch_ups_tc(p, dv.tc_fmt, batch, Fmax, st);
       else launch_conv_tc(p, dv.tc_fmt, batch, Fmax, st);
     } else {
       ConvParams p;

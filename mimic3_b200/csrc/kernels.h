@@ -116,8 +116,9 @@ struct TcConvParams {
 };
 bool conv_tc_supported(int K, int NC, int taps, int dil);
 void launch_conv_tc(const TcConvParams& p, int fmt, int n_seg, int max_seg_len, cudaStream_t st);
-// Staged for round 2 (kernels_tc_ups.cu): the TC_UPS case with a shared-memory bias and an early accumulator
-// release; selected by M3B200_UPS_V2=1 only -- not yet verified on hardware.
+// kernels_tc_ups.cu: the TC_UPS case with a shared-memory bias and an early accumulator release; the default
+// for the polyphase upsamplers since round 2 (bit-identical to conv_tc_kernel's TC_UPS epilogue, which
+// M3B200_UPS_V1=1 selects again).
 bool ups_tc_enabled();
 bool ups_tc_supported(const TcConvParams& p);
 void launch_ups_tc(const TcConvParams& p, int fmt, int n_seg, int max_seg_len, cudaStream_t st);
@@ -146,11 +147,6 @@ bool rowgemm_tc_supported(int K, int taps);
 int rowgemm_tc_nc(int N, int taps);
 size_t rowgemm_tc_weight_elems(int K, int N, int taps, int nc);
 void launch_rowgemm_tc(const RowGemmTcParams& p, cudaStream_t st);
-// Staged for round 2 (kernels_tc_rows2.cu): resident-A variant of the same GEMM on the same packed weights
-// (bit-identical results); selected by M3B200_ROWGEMM_V2=1 only -- not yet verified on hardware.
-bool rowgemm2_enabled();
-bool rowgemm2_supported(const RowGemmTcParams& p);
-void launch_rowgemm2(const RowGemmTcParams& p, cudaStream_t st);
 void launch_fill_vmap(int* vmap, const int* seg_off, const int* seg_len, int n_seg, int max_len, cudaStream_t st);
 
 // Fused last generator stage: ConvTranspose + MRF + conv_post/tanh/peak (kernels_tc_dec.cu).

@@ -1,6 +1,6 @@
 // Polyphase ConvTranspose1d upsampler of the HiFi-GAN generator as an implicit GEMM (sm_100a), second generation.
-// STAGED FOR ROUND 2 -- off by default (M3B200_UPS_V2=1 selects it; tests/test_gpu_experimental.py); it has not run
-// on hardware yet.  Same math, operand layout, weight packing and CTA roles as conv_tc_kernel with the TC_UPS
+// Default for the upsamplers since round 2 (1.22 -> 0.87 ms per step at batch 256, bit-identical on hardware:
+// profiles/r02a_ab_staged_kernels.txt).  Same math, operand layout, weight packing and CTA roles as conv_tc_kernel with the TC_UPS
 // epilogue (kernels_tc_conv.cu):
 //     D[t, ph*Cout + co] = sum_{tap} lrelu(x[t - taps + 1 + tap, :]) . W_tap[:, ph*Cout + co];   y[t*u + ph - pad, co] = D + b[co]
 // What changes is the epilogue, which is what bounds conv_tc_kernel on this shape: the ncu source page of
@@ -215,9 +215,11 @@ __global__ void __launch_bounds__(CT_THREADS, 1) ups_tc_kernel(TcConvParams p, i
 }
 }  // namespace
 
+// Default since round 2 (upsample stage 1.22 -> 0.87 ms, bit-identical; profiles/r02a_ab_staged_kernels.txt).
+// M3B200_UPS_V1=1 selects the generic conv_tc_kernel TC_UPS epilogue again (A/B and the bit-identity test).
 bool ups_tc_enabled() {
-  const char* e = getenv("M3B200_UPS_V2");
-  return e && *e && *e != '0';
+  const char* e = getenv("M3B200_UPS_V1");
+  return !(e && *e && *e != '0');
 }
 
 // Same shapes as conv_tc_supported plus the alignment the 256-bit stores and the float4 bias reads need.

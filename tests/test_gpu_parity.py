@@ -67,6 +67,16 @@ def _compare(sess, orc, ids, lengths, scales, sid=None, seed=0, tol=RMS_TOL):
         assert rms <= tol, f"utt {b}: waveform RMS {rms:.3e} > {tol}"
         np.testing.assert_allclose(r.tensors["x"][tok:tok + L], inter["x"], atol=2e-4, rtol=1e-4)
         np.testing.assert_allclose(r.tensors["logw"][tok:tok + L, 0], inter["logw"], atol=2e-4, rtol=1e-4)
+        # projected prior statistics (m_p | logs_p), the expanded + noised prior z_p and the flow output z:
+        # token rows / frame rows of this utterance in the packed, channels-last engine tensors
+        np.testing.assert_allclose(r.tensors["stats"][tok:tok + L], np.concatenate([inter["m_p"], inter["logs_p"]], 1),
+                                   atol=3e-4, rtol=1e-4, err_msg=f"stats (utt {b})")
+        f0 = int(r.frames[:b].sum())
+        zp, z = r.tensors["z_p"][f0:f0 + r.frames[b]], r.tensors["z"][f0:f0 + r.frames[b]]
+        assert zp.shape == inter["z_p"].shape and z.shape == inter["z"].shape
+        np.testing.assert_allclose(zp, inter["z_p"], atol=1e-3, rtol=1e-4, err_msg=f"z_p (utt {b})")
+        rel = float(np.sqrt(np.mean((z - inter["z"]) ** 2)) / max(1e-12, np.sqrt(np.mean(inter["z"] ** 2))))
+        assert rel <= 5e-3, f"utt {b}: flow output z relative RMS {rel:.3e}"  # fp16 operands, fp32 accumulate
         # the engine's own int16 conversion is bit-exact w.r.t. the reference formula on ITS float audio
         np.testing.assert_array_equal(r.utterance_pcm(b), audio_float_to_int16(got))
         assert abs(float(r.peaks[b]) - float(np.abs(got).max())) == 0.0
@@ -437,3 +447,86 @@ def test_wide_io_is_bit_identical(sessions, monkeypatch):
     alt = tiny.infer(ids, lens, (0.0, 1.0, 0.0), np.array([0, 1]), keep_float=True)
     monkeypatch.delenv("M3B200_WIDE_IO")
     np.testing.assert_array_equal(alt.audio, ref.audio)
+
+
+def test_upsampler_kernel_is_bit_identical_to_generic_conv(sessions, monkeypatch):
+    """ups_tc_kernel (kernels_tc_ups.cu: bias in shared memory, early accumulator release; the default since round 2)
+    computes exactly what conv_tc_kernel's TC_UPS epilogue (M3B200_UPS_V1=1) computes: same MMAs, same `acc + bias`."""
+    rng = np.random.default_rng(2)
+    for voice, nsym, lens_list in (("low_ms", 50, [80, 3, 41, 1, 64, 17, 100]), ("tiny_ms", 20, [9, 30, 1])):
+        sess = sessions(voice)
+        ids, lens = _batch(rng, nsym, lens_list)
+        sid = rng.integers(0, sess.info.n_speakers, size=len(lens_list))
+        new = sess.infer(ids, lens, (0.667, 1.0, 0.8), sid, seed=3, keep_float=True)
+        monkeypatch.setenv("M3B200_UPS_V1", "1")
+        old = sess.infer(ids, lens, (0.667, 1.0, 0.8), sid, seed=3, keep_float=True)
+        monkeypatch.delenv("M3B200_UPS_V1")
+        np.testing.assert_array_equal(new.frames, old.frames)
+        np.testing.assert_array_equal(new.audio, old.audio)
+        np.testing.assert_array_equal(new.pcm, old.pcm)
+
+
+def _compare_rows(sess, orc, ids, lens, sid, scales, seed, rows, tag):
+    """Whole batch through the engine once, the chosen rows one by one through the oracle (batch 1, same Philox
+    stream selected by `row`).  Durations equal, waveform RMS <= 1e-3, PCM == the reference formula on the engine's
+    float audio and within 1 LSB of the oracle's PCM wherever the float waveforms agree to 1e-6."""
+    from oracle.vits_oracle import audio_float_to_int16
+    r = sess.infer(ids, lens, scales, sid, seed=seed, keep_float=True, debug_tensors=("durations", "logw", "z_p", "z", "stats"))
+    tok_off = np.concatenate([[0], np.cumsum(lens)])
+    frm_off = np.concatenate([[0], np.cumsum(r.frames)])
+    worst = 0.0
+    for b in rows:
+        L = int(lens[b])
+        audio, inter = orc.infer(ids[b, :L], scales, sid=None if sid is None else int(sid[b]), seed=seed, row=b,
+                                 return_intermediates=True)
+        t0, f0 = int(tok_off[b]), int(frm_off[b])
+        np.testing.assert_array_equal(r.tensors["durations"][t0:t0 + L, 0].astype(np.int64), inter["durations"],
+                                      err_msg=f"{tag}: durations differ (row {b})")
+        assert r.frames[b] == max(1, int(inter["durations"].sum()))
+        np.testing.assert_allclose(r.tensors["logw"][t0:t0 + L, 0], inter["logw"], atol=2e-4, rtol=1e-4)
+        np.testing.assert_allclose(r.tensors["stats"][t0:t0 + L], np.concatenate([inter["m_p"], inter["logs_p"]], 1),
+                                   atol=3e-4, rtol=1e-4)
+        np.testing.assert_allclose(r.tensors["z_p"][f0:f0 + r.frames[b]], inter["z_p"], atol=1e-3, rtol=1e-4)
+        z = r.tensors["z"][f0:f0 + r.frames[b]]
+        rel = float(np.sqrt(np.mean((z - inter["z"]) ** 2)) / np.sqrt(np.mean(inter["z"] ** 2)))
+        assert rel <= 5e-3, f"{tag} row {b}: z relative RMS {rel:.3e}"
+        got = r.utterance_audio(b)
+        assert got.shape == audio.shape
+        rms = float(np.sqrt(np.mean((got - audio) ** 2)))
+        worst = max(worst, rms)
+        assert rms <= RMS_TOL, f"{tag} row {b}: waveform RMS {rms:.3e}"
+        pcm = r.utterance_pcm(b)
+        np.testing.assert_array_equal(pcm, audio_float_to_int16(got))
+        want = audio_float_to_int16(audio)
+        close = np.abs(got - audio) <= 1e-6
+        if abs(float(np.abs(got).max()) - float(np.abs(audio).max())) <= 1e-6 and close.any():
+            assert np.abs(pcm[close].astype(np.int32) - want[close].astype(np.int32)).max() <= 1
+    return worst, r
+
+
+def test_benchmarked_config3_parity_256x80_all_speakers(sessions, oracles):
+    """The exact batch bench.py times (BASELINE configs[2]: `bench.make_inputs()`: 256 x 80 ids, PCG64(1234),
+    sid = b mod 109, vctk_low-shaped voice) against the oracle: 20 rows spread over the batch and the speakers, at
+    the parity settings (0, 1, 0) and at the voice defaults (0.667, 1, 0.8) with the shared Philox streams."""
+    import bench
+    sess, orc = sessions("low_ms"), oracles("low_ms")
+    ids, lens, sid = bench.make_inputs()
+    assert ids.shape == (256, 80) and int(sid.max()) == 108
+    rows = sorted(set(int(x) for x in np.linspace(0, 255, 18)) | {108, 109})
+    for scales, seed in (((0.0, 1.0, 0.0), 0), ((0.667, 1.0, 0.8), 2001)):
+        worst, r = _compare_rows(sess, orc, ids, lens, sid, scales, seed, rows, f"cfg3 {scales}")
+        print(f"cfg3 {scales}: {len(rows)} rows, worst RMS {worst:.3e}, frames/id {r.frames.sum() / lens.sum():.2f}")
+
+
+def test_benchmarked_config2_parity_32x100_speaker0(sessions, oracles):
+    """BASELINE configs[1]: batch 32 x 100 ids, speaker p239 = index 0 (voices.json:735-736): 16 rows vs the oracle,
+    noise off and on."""
+    sess, orc = sessions("low_ms"), oracles("low_ms")
+    rng = np.random.Generator(np.random.PCG64(1234))
+    ids = rng.integers(4, 50, size=(32, 100)).astype(np.int64)
+    lens = np.full(32, 100, dtype=np.int64)
+    sid = np.zeros(32, dtype=np.int64)
+    rows = list(range(0, 32, 2))
+    for scales, seed in (((0.0, 1.0, 0.0), 0), ((0.667, 1.0, 0.8), 77)):
+        worst, r = _compare_rows(sess, orc, ids, lens, sid, scales, seed, rows, f"cfg2 {scales}")
+        print(f"cfg2 {scales}: {len(rows)} rows, worst RMS {worst:.3e}")
