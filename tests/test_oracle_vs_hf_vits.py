@@ -6,9 +6,11 @@ of the same published VITS inference graph (``transformers/models/vits/modeling_
 jaywalnut310/vits used for MMS-TTS).  Here the SAME synthetic weights are loaded into both the oracle
 (through the voice directory / generator.onnx, like the engine) and ``VitsModel`` (by parameter-name
 mapping), both run the deterministic settings of the reference's golden samples (noise scales 0), and
-durations + waveforms must agree to fp32 noise.  HF implements ResBlock1 generators only, so the voices
-here use ``resblock = "1"``; ResBlock2 (the shipped ``*_low`` voices) differs from it by dropping the second
-conv of every pair and is covered by the oracle's own unit tests.
+durations + waveforms must agree to fp32 noise.  HF implements ResBlock1 generators only
+(``x += conv2(lrelu(conv1(lrelu(x))))``); the shipped ``*_low`` voices use ResBlock2 (``x += conv(lrelu(x))``).
+ResBlock2 is anchored on HF's code too: HF's ``HifiGanResidualBlock.forward`` runs UNMODIFIED with every
+``convs2[i]`` module swapped for the exact inverse of the leaky ReLU that precedes it, which removes the second
+conv and nothing else (``test_oracle_matches_transformers_vits_resblock2*``).
 """
 import numpy as np
 import pytest
@@ -38,6 +40,15 @@ def _hf_model(cfg, params):
         hidden_dropout=0.0, attention_dropout=0.0, activation_dropout=0.0, layerdrop=0.0, layer_norm_eps=1e-5,
         sampling_rate=22050)
     model = VitsModel(hcfg).eval()
+    rb2 = str(cfg.resblock) == "2"
+    if rb2:
+        # ResBlock2 out of HF's ResBlock1 code: conv2(lrelu(t)) becomes t when conv2 := lrelu^-1
+        class InverseLeakyReLU(torch.nn.Module):
+            def forward(self, t):
+                return torch.where(t >= 0, t, t / 0.1)
+        for blk in model.decoder.resblocks:
+            for i in range(len(blk.convs2)):
+                blk.convs2[i] = InverseLeakyReLU()
     sd = model.state_dict()
     used = set()
 
@@ -119,6 +130,9 @@ def _hf_model(cfg, params):
         conv(f"decoder.upsampler.{i}", f"dec.ups.{i}")
         for j in range(nk):
             for d in range(len(cfg.resblock_dilation_sizes[j])):
+                if rb2:
+                    conv(f"decoder.resblocks.{i * nk + j}.convs1.{d}", f"dec.resblocks.{i * nk + j}.convs.{d}")
+                    continue
                 conv(f"decoder.resblocks.{i * nk + j}.convs1.{d}", f"dec.resblocks.{i * nk + j}.convs1.{d}")
                 conv(f"decoder.resblocks.{i * nk + j}.convs2.{d}", f"dec.resblocks.{i * nk + j}.convs2.{d}")
     missing = [k for k in sd if k not in used and not k.startswith(("posterior_encoder.", "duration_predictor.post_"))
@@ -218,3 +232,56 @@ def test_oracle_matches_transformers_vits_at_low_voice_shapes(tmp_path):
     rms = float(np.sqrt(np.mean((audio - want) ** 2)))
     print(f"low shapes: {audio.shape[0]} samples, signal RMS {np.sqrt(np.mean(want ** 2)):.3f}, oracle vs transformers RMS {rms:.2e}")
     assert rms <= 2e-5
+
+
+@pytest.mark.parametrize("n_speakers", [3, 1])
+def test_oracle_matches_transformers_vits_resblock2(tmp_path, n_speakers):
+    """The generator variant every shipped ``*_low`` voice uses (ResBlock2, config.py:128-129 ``resblock: "2"``),
+    anchored on HF's unmodified residual-block forward with the second conv replaced by lrelu^-1 (module docstring)."""
+    torch = pytest.importorskip("torch")
+    pytest.importorskip("transformers")
+    from oracle.vits_oracle import VitsOracle
+
+    cfg = sv.tiny_config(n_speakers=n_speakers, resblock="2", use_sdp=True)
+    params = sv.write_voice(tmp_path / "v", cfg, seed=6)
+    assert any(".convs.0.weight" in k for k in params) and not any(".convs1." in k for k in params)
+    orc = VitsOracle(str(tmp_path / "v"))
+    hf = _hf_model(cfg, params)
+    rng = np.random.default_rng(19)
+    for T, length_scale, sid in ((23, 1.0, 0), (7, 1.3, n_speakers - 1), (40, 0.8, 0), (1, 1.0, 0)):
+        ids = rng.integers(4, cfg.num_symbols, size=T).astype(np.int64)
+        audio = orc.infer(ids, (0.0, length_scale, 0.0), sid=sid if n_speakers > 1 else None)
+        hf.noise_scale, hf.noise_scale_duration, hf.speaking_rate = 0.0, 0.0, 1.0 / length_scale
+        with torch.no_grad():
+            out = hf(input_ids=torch.from_numpy(ids)[None], attention_mask=torch.ones(1, T, dtype=torch.long),
+                     speaker_id=sid if n_speakers > 1 else None)
+        want = out.waveform[0].numpy()
+        assert int(out.sequence_lengths[0]) == audio.shape[0] == want.shape[0]
+        rms = float(np.sqrt(np.mean((audio - want) ** 2)))
+        sig = float(np.sqrt(np.mean(want ** 2)))
+        assert rms <= 2e-5 * max(1.0, sig / 0.1), (T, rms, sig)
+
+
+def test_oracle_matches_transformers_vits_resblock2_at_low_voice_shapes(tmp_path):
+    """ResBlock2 at the exact shapes of the benchmarked voice (`sv.low_config(n_speakers=109)`, the configuration
+    bench.py and the GPU parity tests use): the oracle the CUDA path is compared with is itself compared with HF."""
+    torch = pytest.importorskip("torch")
+    pytest.importorskip("transformers")
+    from oracle.vits_oracle import VitsOracle
+
+    cfg = sv.low_config(n_speakers=109)
+    assert str(cfg.resblock) == "2"
+    params = sv.write_voice(tmp_path / "v", cfg, seed=22)
+    orc = VitsOracle(str(tmp_path / "v"))
+    hf = _hf_model(cfg, params)
+    ids = np.random.default_rng(5).integers(4, cfg.num_symbols, size=40).astype(np.int64)
+    for sid in (0, 108):
+        audio = orc.infer(ids, (0.0, 1.0, 0.0), sid=sid)
+        hf.noise_scale, hf.noise_scale_duration, hf.speaking_rate = 0.0, 0.0, 1.0
+        with torch.no_grad():
+            out = hf(input_ids=torch.from_numpy(ids)[None], attention_mask=torch.ones(1, 40, dtype=torch.long), speaker_id=sid)
+        want = out.waveform[0].numpy()
+        assert want.shape == audio.shape and audio.shape[0] % 256 == 0
+        rms = float(np.sqrt(np.mean((audio - want) ** 2)))
+        print(f"low shapes, ResBlock2, sid {sid}: {audio.shape[0]} samples, oracle vs transformers RMS {rms:.2e}")
+        assert rms <= 2e-5
