@@ -2,16 +2,23 @@
 """Benchmark of the ids->waveform hot path (contract: see the task description / DESIGN.md §5).
 
     python bench.py --gpus N --steps K --warmup W            # the CUDA engine (libm3b200)
-    python bench.py --impl reference --gpus N --steps K ...    # the CPU path (oracle port), rank 0 only
+    python bench.py --impl reference --gpus N --steps K ...    # the CPU path, rank 0 only
 
-Workload = BASELINE.json configs[2] (the one the metric is quoted on): an en_US/vctk_low-shaped
+Default workload = BASELINE.json configs[2] (the one the metric is quoted on): an en_US/vctk_low-shaped
 voice (109 speakers, synthetic random weights -- no real voice is reachable offline), batch 256,
-80 ids per utterance, sid[b] = b mod 109, PCG64(1234).  Utterances are independent, so every rank
-runs this workload on its own rows with no collective on the compute path: by default per-GPU
-work is fixed (weak scaling, global batch 256 x N, as the bench contract prescribes for a path
-that partitions); ``--scaling strong`` shards ONE batch of 256 over the N ranks instead
-(BASELINE configs[2] literally: 32 utterances per GPU at N = 8).  A "step" = one pass of the hot
-path over the whole (global) batch.  Prints ONE JSON line on rank 0.
+80 ids per utterance, sid[b] = b mod 109, PCG64(1234).  ``--workload cfg2|cfg4|cfg5`` select the other
+BASELINE configs (profiles/ lines, not the headline).  Utterances are independent, so every rank runs
+its own rows with no collective on the compute path: by default per-GPU work is fixed (weak scaling,
+global batch 256 x N, as the bench contract prescribes for a path that partitions); ``--scaling strong``
+shards ONE batch over the N ranks instead (BASELINE configs[2] literally: 32 utterances per GPU at N = 8).
+A "step" = one pass of the hot path over the whole (global) batch.  Prints ONE JSON line on rank 0.
+
+Two timed regions:
+  value  ids already resident in HBM, PCM left in HBM (kernel-resident throughput);
+  e2e    host ids -> engine -> int16 PCM in (pinned) host memory on rank 0.  N>1: rank 0 scatters the ids
+         (pinned H2D + NCCL) and gathers the PCM (NCCL send/recv + one D2H) every step
+         (mimic3_b200/shard.py); the gather + D2H of step k overlap the compute of step k+1 (two slots),
+         every byte of every step has landed on the host before the closing timestamp.
 """
 from __future__ import annotations
 
@@ -23,6 +30,7 @@ import sys
 import tempfile
 import threading
 import time
+from collections import deque
 from pathlib import Path
 
 import numpy as np
@@ -37,28 +45,72 @@ NUM_SYMBOLS = 50
 VOICE_SEED = 22
 METRIC = "audio samples/s (en_US/vctk_low batch=256)"
 
+# name -> (sub-directory, speakers, symbols, seed): synthetic stand-ins with the shipped voices' shapes
+VOICES = {
+    "vctk_low": ("en_US/vctk_low", N_SPEAKERS, NUM_SYMBOLS, VOICE_SEED),
+    "thorsten_low": ("de_DE/thorsten_low", 1, 56, 23),
+    "siwis_low": ("fr_FR/siwis_low", 1, 44, 24),
+}
+
 
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
-def make_voice(root: Path) -> Path:
-    """Synthetic vctk_low-shaped voice; written by local rank 0, shared through the filesystem."""
+def make_voice(root: Path, name: str = "vctk_low") -> Path:
+    """Synthetic <name>-shaped voice; written by local rank 0, shared through the filesystem."""
     from mimic3_b200 import synth_voice as sv
-    d = root / "en_US" / "vctk_low"
+    sub, nspk, nsym, seed = VOICES[name]
+    d = root / sub
     marker = d / ".complete"
     if not marker.exists():
-        sv.write_voice(d, sv.low_config(n_speakers=N_SPEAKERS, num_symbols=NUM_SYMBOLS), seed=VOICE_SEED)
+        sv.write_voice(d, sv.low_config(n_speakers=nspk, num_symbols=nsym), seed=seed)
         marker.write_text("ok")
     return d
 
 
-def make_inputs(batch: int = GLOBAL_BATCH):
+def make_inputs(batch: int = GLOBAL_BATCH, ids_per_utt: int = IDS_PER_UTT, num_symbols: int = NUM_SYMBOLS,
+                n_speakers: int = N_SPEAKERS, all_speakers: bool = True):
+    """PCG64(1234), fixed-length rows, ids uniform over the real symbols (pad/bos/eos/blank = 0..3
+    excluded), sid = b mod n_speakers (cfg3) or 0 (cfg2: p239 is index 0, voices.json:735-736)."""
     rng = np.random.Generator(np.random.PCG64(1234))
-    ids = rng.integers(4, NUM_SYMBOLS, size=(batch, IDS_PER_UTT)).astype(np.int64)  # pad/bos/eos/blank excluded
-    lengths = np.full(batch, IDS_PER_UTT, dtype=np.int64)
-    sid = (np.arange(batch) % N_SPEAKERS).astype(np.int64)
+    ids = rng.integers(4, num_symbols, size=(batch, ids_per_utt)).astype(np.int64)
+    lengths = np.full(batch, ids_per_utt, dtype=np.int64)
+    sid = (np.arange(batch) % n_speakers).astype(np.int64) if all_speakers else np.zeros(batch, dtype=np.int64)
     return ids, lengths, sid
+
+
+def make_jobs(workload: str, batch: int):
+    """One step = these engine calls, in order: dicts(voice, ids, lengths, sid|None, scales|None=voice defaults)."""
+    if workload == "cfg3":
+        ids, lengths, sid = make_inputs(batch)
+        return [dict(voice="vctk_low", ids=ids, lengths=lengths, sid=sid, scales=None)]
+    if workload == "cfg2":   # B=32 x 100 ids, speaker p239 (index 0)
+        ids, lengths, sid = make_inputs(batch, 100, all_speakers=False)
+        return [dict(voice="vctk_low", ids=ids, lengths=lengths, sid=sid, scales=None)]
+    if workload == "cfg4":   # long form: B=8 x 1800 ids, single-speaker voice, three length scales per step
+        ids, lengths, _ = make_inputs(batch, 1800, VOICES["thorsten_low"][2])
+        return [dict(voice="thorsten_low", ids=ids, lengths=lengths, sid=None, scales=(0.667, ls, 0.8))
+                for ls in (0.8, 1.0, 1.2)]
+    if workload == "cfg5":   # mixed voices, rows grouped by voice (43/43/42 of 128), all three resident
+        names = ["vctk_low", "thorsten_low", "siwis_low"]
+        base, extra = divmod(batch, 3)
+        jobs = []
+        for i, n in enumerate(names):
+            rows = base + (1 if i < extra else 0)
+            ids, lengths, sid = make_inputs(rows, IDS_PER_UTT, VOICES[n][2], VOICES[n][1])
+            jobs.append(dict(voice=n, ids=ids, lengths=lengths, sid=sid if VOICES[n][1] > 1 else None, scales=None))
+        return jobs
+    raise SystemExit(f"unknown workload {workload}")
+
+
+WORKLOAD_TEXT = {
+    "cfg3": "configs[2]: vctk_low-shaped synthetic voice (109 speakers, random weights), {b} x 80 ids, sid=b%109",
+    "cfg2": "configs[1]: vctk_low-shaped synthetic voice, speaker index 0 (p239), {b} x 100 ids",
+    "cfg4": "configs[3]: thorsten_low-shaped synthetic voice (single speaker), {b} x 1800 ids, one pass per length_scale in (0.8, 1.0, 1.2) per step",
+    "cfg5": "configs[4]: mixed batch of {b} x 80 ids over three resident voices (vctk_low 109 spk / thorsten_low / siwis_low), rows grouped by voice, one engine call per voice per step",
+}
+DEFAULT_BATCH = {"cfg3": 256, "cfg2": 32, "cfg4": 8, "cfg5": 128}
 
 
 class ClockSampler:
@@ -136,12 +188,81 @@ def algorithmic_flops_per_frame(cfg) -> dict:
     return out
 
 
+def probe_reference_stack() -> dict:
+    """BASELINE.md §3.1 / SURVEY §7 step 0, performed at RUN TIME on the box the numbers come from: is the
+    reference's own arithmetic (onnxruntime + a real generator.onnx) reachable here?  The result is printed in the
+    bench line; the CPU arm uses onnxruntime when the probe finds it, else the oracle port (kind "port")."""
+    out = {"onnxruntime": None, "baseline_ref": False, "mimic3_tts": False, "voices_found": [], "searched": []}
+    ref = ROOT / "baseline" / "_ref"
+    out["baseline_ref"] = ref.is_dir()
+    if ref.is_dir() and str(ref) not in sys.path:
+        sys.path.append(str(ref))
+    try:
+        import onnxruntime  # noqa: F401
+        out["onnxruntime"] = getattr(onnxruntime, "__version__", "?")
+    except Exception as e:
+        out["onnxruntime_error"] = type(e).__name__
+    try:
+        import importlib.util
+        out["mimic3_tts"] = importlib.util.find_spec("mimic3_tts") is not None
+    except Exception:
+        pass
+    dirs = []
+    home = os.environ.get("XDG_DATA_HOME") or os.path.join(os.path.expanduser("~"), ".local", "share")
+    dirs.append(Path(home) / "mycroft" / "mimic3" / "voices")                # const.py:25-27
+    for d in (os.environ.get("XDG_DATA_DIRS") or "/usr/local/share:/usr/share").split(":"):
+        if d:
+            dirs.append(Path(d) / "mycroft" / "mimic3" / "voices")          # tts.py:160-181
+    dirs.append(ref / "voices")
+    for d in dirs:
+        out["searched"].append(str(d))
+        try:
+            if d.is_dir():
+                out["voices_found"] += [str(p.parent) for p in sorted(d.glob("*/*/generator.onnx"))][:8]
+        except OSError:
+            pass
+    return out
+
+
+def ort_cpu_baseline(probe: dict, n_utts: int):
+    """The reference's own CPU path, if the probe found it: onnxruntime CPUExecutionProvider, default session
+    options, B=1 loop, timed like voice.py:229-232 (run + audio_float_to_int16).  Returns None when unavailable."""
+    if not probe.get("onnxruntime") or not probe.get("voices_found"):
+        return None
+    import onnxruntime
+    vd = Path(next((v for v in probe["voices_found"] if v.endswith("vctk_low")), probe["voices_found"][0]))
+    cfgj = json.loads((vd / "config.json").read_text())
+    sess = onnxruntime.InferenceSession(str(vd / "generator.onnx"), providers=["CPUExecutionProvider"])
+    names = {i.name for i in sess.get_inputs()}
+    nsym = int(cfgj["model"]["num_symbols"])
+    nspk = int(cfgj["model"].get("n_speakers", 1))
+    inf = cfgj.get("inference", {})
+    scales = np.array([inf.get("noise_scale", 0.667), inf.get("length_scale", 1.0), inf.get("noise_w", 0.8)], dtype=np.float32)
+    ids, lengths, sid = make_inputs(n_utts, IDS_PER_UTT, nsym, max(nspk, 1))
+
+    def one(b):
+        feed = {"input": ids[b:b + 1], "input_lengths": lengths[b:b + 1], "scales": scales}
+        if "sid" in names:
+            feed["sid"] = sid[b:b + 1]
+        audio = sess.run(None, feed)[0].squeeze()
+        peak = max(0.01, float(np.max(np.abs(audio))))
+        return np.clip(audio * (32767.0 / peak), -32767, 32767).astype("int16").size
+    for b in range(min(3, n_utts)):
+        one(b)
+    t0 = time.perf_counter()
+    n = sum(one(b) for b in range(n_utts))
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": "samples/s", "cores": os.cpu_count(), "kind": "reference",
+            "sample": f"onnxruntime {probe['onnxruntime']} CPUExecutionProvider on {vd}, {n_utts} utterances x 80 ids, "
+                      f"batch-1 loop ({dt:.1f} s), default session options"}
+
+
 def run_reference(args, rank: int, world: int):
-    """CPU arm: the oracle port (kind "port": onnxruntime + generator.onnx are unobtainable offline)
+    """CPU arm: onnxruntime if the run-time probe finds it (kind "reference"), else the oracle port (kind "port")
     on rank 0's host cores, B=1 loop like the reference (voice.py:180-181), bounded sample per step."""
     if rank != 0:
         return
-    import torch
+    probe = probe_reference_stack()
     from oracle.vits_oracle import VitsOracle, audio_float_to_int16
     with tempfile.TemporaryDirectory() as d:
         vd = make_voice(Path(d))
@@ -163,18 +284,38 @@ def run_reference(args, rank: int, world: int):
         total = sum(step(args.warmup + k) for k in range(args.steps))
         dt = time.perf_counter() - t0
     value = total / dt
+    base = {"value": value, "unit": "samples/s", "cores": cores, "kind": "port",
+            "sample": f"{sample} utterances/step x {args.steps} steps, torch fp32 CPU, {cores} threads"}
+    try:
+        ort = ort_cpu_baseline(probe, sample * args.steps)
+    except Exception as e:
+        ort = None
+        probe["ort_run_error"] = repr(e)
+    if ort:
+        base, value = ort, ort["value"]
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "configs[2]: vctk_low-shaped synthetic voice, 109 speakers, batch=256 x 80 ids",
                    "sample": f"{sample} utterances of the batch per step, batch-1 loop"},
-        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port",
-                         "sample": f"{sample} utterances/step x {args.steps} steps, torch fp32 CPU, {cores} threads"},
+        "cpu_baseline": base, "reference_probe": probe,
         "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def measured_traffic(kernel: str):
+    """DRAM read+write bytes per processed audio sample of `kernel`, from the newest committed ncu capture
+    (profiles/traffic.json, written by tools/summarize_ncu.py --traffic from a `ncu --set full` run of this
+    bench command); None when no capture has been summarised."""
+    try:
+        t = json.loads((ROOT / "profiles" / "traffic.json").read_text())
+        e = t.get(kernel)
+        return (float(e["dram_bytes_per_sample"]), e.get("source")) if e else (None, None)
+    except Exception:
+        return None, None
 
 
 def main():
@@ -183,15 +324,19 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg3", choices=["cfg2", "cfg3", "cfg4", "cfg5"])
     ap.add_argument("--ref-utts", type=int, default=32, help="utterances per step for the CPU arm")
     ap.add_argument("--cpu-baseline-utts", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--deterministic", action="store_true", help="noise scales 0 (parity settings)")
-    ap.add_argument("--batch", type=int, default=GLOBAL_BATCH, help="batch override (profiling runs only)")
+    ap.add_argument("--batch", type=int, default=0, help="batch override (0 = the workload's own batch)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: --batch utterances PER GPU (default); strong: --batch utterances sharded over all GPUs")
     ap.add_argument("--profile-only", action="store_true", help="skip stage/e2e/cpu passes (ncu runs)")
+    ap.add_argument("--e2e-depth", type=int, default=2, help="slots of the PCM collector (1 = no overlap of gather/D2H with compute)")
     args = ap.parse_args()
+    if not args.batch:
+        args.batch = DEFAULT_BATCH[args.workload]
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -213,65 +358,103 @@ def main():
         log(f"[bench] note: --gpus {args.gpus} but WORLD_SIZE {world}; using WORLD_SIZE")
     from mimic3_b200.engine import B200Session, STAGES
     from mimic3_b200 import synth_voice as sv
+    from mimic3_b200.shard import shard_bounds
 
-    # -- voice: written once (rank 0), read by every rank ---------------------------------
+    # -- jobs of one step: every rank builds the same global jobs, then keeps its rows ----------------------
+    GB = args.batch * world if args.scaling == "weak" else args.batch  # global batch of one step
+    jobs = make_jobs(args.workload, GB)
+
+    # -- voices: written once (local rank 0), read by every rank; all stay resident -------------------------
     shared = Path(os.environ.get("M3B200_BENCH_DIR", tempfile.gettempdir())) / f"m3b200_bench_voice_{os.environ.get('MASTER_PORT', 'single')}"
+    names = sorted({j["voice"] for j in jobs})
     if local_rank == 0:
-        make_voice(shared)
+        for n in names:
+            make_voice(shared, n)
     if distributed:
         dist.barrier()
-    vd = make_voice(shared)
-    sess = B200Session(str(vd), device=local_rank)
+    sessions = {n: B200Session(str(make_voice(shared, n)), device=local_rank) for n in names}
+    vd = make_voice(shared, "vctk_low") if "vctk_low" in names else None
     cfg = sv.low_config(n_speakers=N_SPEAKERS, num_symbols=NUM_SYMBOLS)
-    scales = (0.0, 1.0, 0.0) if args.deterministic else (sess.info.noise_scale, sess.info.length_scale, sess.info.noise_w)
 
-    # -- inputs: rank r owns rows [r*B/N, (r+1)*B/N) ------------------------------------------
-    GB = args.batch * world if args.scaling == "weak" else args.batch  # global batch of one step
-    ids, lengths, sid = make_inputs(GB)
-    per = GB // world
-    lo, hi = rank * per, (rank + 1) * per if rank < world - 1 else GB
-    my_lengths, my_sid = lengths[lo:hi], sid[lo:hi]
-    if distributed:
-        # NCCL scatter of the padded id tensor from rank 0 (north_star: the only collectives on the
-        # path are the id scatter and the PCM gather)
-        from mimic3_b200.shard import gather_pcm, scatter_ids, shard_bounds
-        lo, hi = shard_bounds(GB, world, rank)
-        d_ids, d_len, d_sid = scatter_ids(ids if rank == 0 else None, lengths if rank == 0 else None,
-                                          sid if rank == 0 else None, torch.device("cuda", local_rank))
-        my_lengths, my_sid = d_len.cpu().numpy(), d_sid.cpu().numpy()
-    else:
-        d_ids = torch.from_numpy(ids[lo:hi]).cuda()
-    h_ids = np.ascontiguousarray(ids[lo:hi])
+    dev = torch.device("cuda", local_rank)
+    for j in jobs:
+        s = sessions[j["voice"]]
+        j["sess"] = s
+        if j["scales"] is None:
+            j["scales"] = (s.info.noise_scale, s.info.length_scale, s.info.noise_w)
+        if args.deterministic:
+            j["scales"] = (0.0, j["scales"][1], 0.0)
+        lo, hi = shard_bounds(j["ids"].shape[0], world, rank)
+        j["lo"], j["hi"] = lo, hi
+        j["my_lengths"] = j["lengths"][lo:hi]
+        j["my_sid"] = None if j["sid"] is None else j["sid"][lo:hi]
+        j["h_ids"] = np.ascontiguousarray(j["ids"][lo:hi])
+        j["d_ids"] = torch.from_numpy(j["h_ids"]).cuda() if hi > lo else None
+        j["T"] = int(j["ids"].shape[1])
     torch.cuda.synchronize()
 
     def step_resident(seed, timing=False):
-        return sess.infer(IDS_PER_UTT, my_lengths, scales, my_sid, seed=seed, host_copy=False,
-                          device_ids_ptr=d_ids.data_ptr(), stage_timing=timing)
+        out = []
+        for j in jobs:
+            if j["hi"] == j["lo"]:
+                continue
+            out.append(j["sess"].infer(j["T"], j["my_lengths"], j["scales"], j["my_sid"], seed=seed, host_copy=False,
+                                       device_ids_ptr=j["d_ids"].data_ptr(), stage_timing=timing))
+        return out
 
-    pcm_dev = torch.empty(1, dtype=torch.int16, device="cuda")
+    # -- end to end: host ids in, int16 PCM back on the host ---------------------------------------------------
+    scat = coll = None
+    if distributed and not args.profile_only:
+        from mimic3_b200.shard import IdScatter, PcmCollector, make_groups
+        gather_pg, meta_pg = make_groups(dev)
+        max_rows = max(j["ids"].shape[0] for j in jobs)
+        max_t = max(j["T"] for j in jobs)
+        per = (max_rows + world - 1) // world
+        scat = IdScatter(max_rows, max_t, dev, payload_group=None, meta_group=meta_pg)
+        # capacity: generous bound per rank (ids x 12 frames/id x hop); the synthetic voices give 4-5 frames per id
+        cap = per * max_t * 12 * 256
+        coll = PcmCollector(cap, per, dev, payload_group=gather_pg, meta_group=meta_pg, depth=max(1, args.e2e_depth))
+    tickets = deque()
+
+    def e2e_collect(t):
+        got = coll.collect(t)
+        if got is None:
+            return 0
+        pcm, frames = got
+        n = int(sum(int(np.sum(f)) for f in frames)) * 256
+        assert pcm.shape[0] == n, (pcm.shape, n)
+        return n
 
     def step_e2e(seed):
-        """Host ids in, int16 PCM back on the host.  N>1: rank 0 owns the host buffers; ids are
-        scattered and PCM gathered over NCCL, then rank 0 copies to (pinned) host memory."""
-        nonlocal pcm_dev
-        if not distributed:
-            r = sess.infer(h_ids, my_lengths, scales, my_sid, seed=seed, copy=False)  # PCM lands in pinned host memory
-            n = r.total_samples
-            assert r.pcm.shape[0] == n
-            r.close()
-            return n
-        di, dl, ds = scatter_ids(ids if rank == 0 else None, lengths if rank == 0 else None,
-                                 sid if rank == 0 else None, torch.device("cuda", local_rank))
-        cap = int(dl.sum().item()) * 64 * sess.info.hop_length  # generous bound on samples
-        if pcm_dev.numel() < cap:
-            pcm_dev = torch.empty(cap, dtype=torch.int16, device="cuda")
-        r = sess.infer(IDS_PER_UTT, dl.cpu().numpy(), scales, ds.cpu().numpy(), seed=seed, host_copy=False,
-                       device_ids_ptr=di.data_ptr(), device_pcm_out=pcm_dev)
-        out = gather_pcm(pcm_dev[: r.total_samples], r.sample_offsets, torch.device("cuda", local_rank))
-        if rank == 0:
-            host = [b.cpu() for b in out[0]]
-            return sum(int(h.numel()) for h in host)
-        return 0
+        """N=1: `m3_infer` with host ids, PCM lands in pinned host memory.  N>1: rank 0 owns the host buffers."""
+        n = 0
+        for j in jobs:
+            if not distributed:
+                r = j["sess"].infer(j["h_ids"], j["my_lengths"], j["scales"], j["my_sid"], seed=seed, copy=False)
+                n += r.total_samples
+                assert r.pcm.shape[0] == r.total_samples
+                r.close()
+                continue
+            d_ids, lens, sids = scat(j["ids"] if rank == 0 else None, j["lengths"] if rank == 0 else None,
+                                     j["sid"] if rank == 0 else None)
+            buf = coll.send_buffer()
+            if len(lens):
+                r = j["sess"].infer(d_ids.stride(0), lens, j["scales"], sids, seed=seed, host_copy=False,
+                                    device_ids_ptr=d_ids.data_ptr(), device_pcm_out=buf)
+                tickets.append(coll.submit(r.total_samples, r.frames))
+            else:
+                tickets.append(coll.submit(0, []))
+            while len(tickets) >= max(1, args.e2e_depth):
+                n += e2e_collect(tickets.popleft())
+        return n
+
+    def e2e_drain():
+        n = 0
+        while tickets:
+            n += e2e_collect(tickets.popleft())
+        if coll:
+            coll.drain()
+        return n
 
     def sync_all():
         torch.cuda.synchronize()
@@ -289,11 +472,11 @@ def main():
     dev_ms = 0.0
     frames = 0
     for k in range(args.steps):
-        r = step_resident(2000 + k)
-        samples += r.total_samples
-        frames += int(r.frames.sum())
-        launches += r.launches
-        dev_ms += r.device_ms
+        for r in step_resident(2000 + k):
+            samples += r.total_samples
+            frames += int(r.frames.sum())
+            launches += r.launches
+            dev_ms += r.device_ms
     sync_all()
     wall = time.perf_counter() - t0
     clocks = sampler.stop() if sampler else None
@@ -307,20 +490,22 @@ def main():
                               "ms_per_step": wall / args.steps * 1e3}), flush=True)
         return
     for k in range(args.steps):
-        r = step_resident(2000 + k, timing=True)
-        st_frames += int(r.frames.sum())
-        for s in STAGES:
-            if "ms:" + s in r.tensors:
-                stage_ms[s] += float(r.tensors["ms:" + s][0, 0])
+        for r in step_resident(2000 + k, timing=True):
+            st_frames += int(r.frames.sum())
+            for s in STAGES:
+                if "ms:" + s in r.tensors:
+                    stage_ms[s] += float(r.tensors["ms:" + s][0, 0])
 
-    # ---- end to end through the public call: host ids in, int16 PCM back on the host -------------
+    # ---- end to end through the public call ---------------------------------------------------------------
     for k in range(2):
         step_e2e(3000 + k)
+    e2e_drain()
     sync_all()
     t1 = time.perf_counter()
     e2e_samples = 0
     for k in range(args.steps):
         e2e_samples += step_e2e(2000 + k)
+    e2e_samples += e2e_drain()
     sync_all()
     e2e_wall = time.perf_counter() - t1
 
@@ -347,48 +532,62 @@ def main():
         peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
         dec_ms = stage_ms.get("dec_last", 0.0) / args.steps
         mrf_ms = stage_ms["mrf"] / args.steps
+        traffic = traffic_src = None
         if dec_ms > 0:   # dominant kernel: the fused last generator stage (upsample + MRF + conv_post)
             k_name = "dec_fused_kernel (ConvTranspose + MRF + conv_post, last generator stage)"
             k_flops = (fl["ups_stage"][-1] + fl["mrf_stage"][-1] + fl["post"]) * frames_ps
             k_ms = dec_ms
-            traffic = 397.0e6 * (GB / 64.0) / world  # dram read+write of one launch, ncu --set full at batch 64 (profiles/r01b_ncu_full_ws_kernels.md), scaled to this batch
+            per_sample, traffic_src = measured_traffic("dec_fused_kernel")
+            if per_sample is not None:
+                traffic = per_sample * frames_ps * 256
         else:
-            k_name, k_flops, k_ms, traffic = "MRF stages (mrf_tc_kernel x3)", fl["mrf"] * frames_ps, mrf_ms, None
+            k_name, k_flops, k_ms = "MRF stages (mrf_tc_kernel x3)", fl["mrf"] * frames_ps, mrf_ms
         achieved_tf = k_flops / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
         mrf_all_tf = fl["mrf"] * frames_ps / ((mrf_ms + dec_ms) * 1e-3) / 1e12 if (mrf_ms + dec_ms) > 0 else 0.0
+        h2d = sum(int(j["ids"].size * 8 + j["ids"].shape[0] * 16) for j in jobs)
         line = {
             "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": wall_max / args.steps * 1e3, "higher_is_better": True,
             "scaling": args.scaling, "vs_baseline": None,
             "dtype": "fp16 tensor-core operands + fp32 accumulate/residual (flow, decoder); f32 (text encoder, durations)",
             "data": "synthetic",
-            "config": {"workload": "configs[2]: vctk_low-shaped synthetic voice (109 speakers, random weights), "
-                                   + (f"{args.batch} x 80 ids per GPU (weak scaling: global batch {GB}), sid=b%109"
-                                      if args.scaling == "weak" else
-                                      f"one batch of {GB} x 80 ids sharded by rows over the ranks (strong scaling), sid=b%109"),
-                       "global_batch": GB, "ids_per_utterance": IDS_PER_UTT,
-                       "scales": [float(s) for s in scales], "parallelism": f"batch-shard x{world}",
+            "config": {"workload": WORKLOAD_TEXT[args.workload].format(b=GB)
+                                   + (f"; {args.batch} rows per GPU (weak scaling: global batch {GB})" if args.scaling == "weak"
+                                      else f"; one batch of {GB} rows sharded over the ranks (strong scaling)"),
+                       "global_batch": GB, "ids_per_utterance": jobs[0]["T"],
+                       "scales": [[float(s) for s in j["scales"]] for j in jobs] if len(jobs) > 1 else [float(s) for s in jobs[0]["scales"]],
+                       "parallelism": f"batch-shard x{world}",
                        "frames_per_step": tot_frames / args.steps, "samples_per_step": tot_samples / args.steps,
                        "l2": "no flush: per-step activations (GBs) exceed the 126 MB L2 many times over",
                        "timing": "wall clock between barrier+synchronize pairs (>= CUDA-event time), max over ranks",
-                       "device_event_ms_per_step": dev_max / args.steps * 1e3},
+                       "device_event_ms_per_step": dev_max / args.steps * 1e3,
+                       "e2e_pipeline": (f"N>1: id scatter (pinned H2D + NCCL) and PCM gather (NCCL send/recv + one D2H to pinned memory on "
+                                        f"rank 0) every step, {max(1, args.e2e_depth)} slots: step k's gather/D2H overlap step k+1's compute")
+                                       if distributed else "N=1: m3_infer with host ids, PCM copied to pinned host memory inside the call"},
             "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
             "roofline": {"kernel": k_name, "bound": "tensor", "achieved": achieved_tf,
                          "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf if peak_tf else None,
-                         "traffic": traffic,
+                         "traffic": traffic, "traffic_source": traffic_src,
                          "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (fp16 = same tensor rate)" if peaks else "fallback 1400",
                          "kernel_ms": k_ms, "kernel_algorithmic_tflop": k_flops / 1e12,
                          "all_mrf_stages_tflops": mrf_all_tf,
                          "note": "smem operand fetch caps SS-mode MMAs at N=32 to 40 % of the tensor peak (DESIGN.md §3)"},
             "e2e": {"value": tot_e2e / e2e_max, "unit": "samples/s",
-                    "h2d_bytes_per_step": int(GB * IDS_PER_UTT * 8 + GB * 16),
-                    "d2h_bytes_per_step": int(tot_e2e / args.steps * 2)},
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(tot_e2e / args.steps * 2),
+                    "ms_per_step": e2e_max / args.steps * 1e3},
             "gpu_launches": int(tot_launch),
             "clocks": clocks,
+            "reference_probe": probe_reference_stack(),
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and vd is not None:
+            j0 = next(j for j in jobs if j["voice"] == "vctk_low")
             try:
-                line["cpu_baseline"] = cpu_baseline(vd, ids, sid, scales, args.cpu_baseline_utts)
+                ort = ort_cpu_baseline(line["reference_probe"], args.cpu_baseline_utts)
+            except Exception as e:
+                ort = None
+                line["reference_probe"]["ort_run_error"] = repr(e)
+            try:
+                line["cpu_baseline"] = ort or cpu_baseline(vd, j0["ids"], j0["sid"], j0["scales"], args.cpu_baseline_utts)
             except Exception as e:  # the CPU leg must never cost the GPU line
                 line["cpu_baseline"] = {"value": None, "unit": "samples/s", "cores": 0, "kind": "port",
                                         "sample": f"failed: {e!r}"}
@@ -426,6 +625,7 @@ def cpu_baseline(vd, ids, sid, scales, n_utts):
     from oracle.vits_oracle import VitsOracle, audio_float_to_int16
     orc = VitsOracle(str(vd))
     threads, tried = pick_cpu_threads(orc, ids, sid, scales)
+    n_utts = min(n_utts, ids.shape[0])
     t0 = time.perf_counter()
     n = 0
     for b in range(n_utts):

@@ -34,7 +34,9 @@ class FakeSession:
         return FakeResult(len(lengths), stage_timing)
 
 
-@pytest.mark.parametrize("extra", [[], ["--scaling", "strong", "--no-cpu-baseline"], ["--profile-only"]])
+@pytest.mark.parametrize("extra", [[], ["--scaling", "strong", "--no-cpu-baseline"], ["--profile-only"],
+                                   ["--workload", "cfg2", "--no-cpu-baseline"], ["--workload", "cfg4", "--no-cpu-baseline"],
+                                   ["--workload", "cfg5", "--no-cpu-baseline"]])
 def test_gpu_arm_runs_end_to_end_with_a_fake_engine(extra, monkeypatch, tmp_path):
     import torch
     import bench
@@ -70,5 +72,7 @@ def test_gpu_arm_runs_end_to_end_with_a_fake_engine(extra, monkeypatch, tmp_path
     assert d["config"]["global_batch"] == 8 and "workload" in d["config"]
     assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(d["roofline"])
     assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(d["e2e"])
-    assert d["gpu_launches"] == 2 * 110 and d["e2e"]["value"] > 0
+    calls = 3 if ("cfg4" in extra or "cfg5" in extra) else 1      # engine calls per step
+    assert d["gpu_launches"] == 2 * 110 * calls and d["e2e"]["value"] > 0
+    assert "reference_probe" in d and "onnxruntime" in d["reference_probe"]
     assert ("cpu_baseline" in d) == ("--no-cpu-baseline" not in extra)

@@ -31,41 +31,74 @@ def _worker(rank, world, port, tmp):
     sys.path.insert(0, str(ROOT))
     import torch
     import torch.distributed as dist
-    from mimic3_b200.shard import gather_pcm, scatter_ids, shard_bounds
+    from mimic3_b200.shard import IdScatter, PcmCollector, make_groups, shard_bounds
     dist.init_process_group("gloo", rank=rank, world_size=world)
+    pg, mg = make_groups("cpu")
     B, T = 7, 11
-    rng = np.random.default_rng(0)
-    ids = rng.integers(4, 50, size=(B, T)).astype(np.int64)
-    lengths = rng.integers(1, T + 1, size=B).astype(np.int64)
-    sid = (np.arange(B) % 3).astype(np.int64)
-    got = scatter_ids(ids if rank == 0 else None, lengths if rank == 0 else None, sid if rank == 0 else None, "cpu")
-    lo, hi = shard_bounds(B, world, rank)
-    assert np.array_equal(got[0].numpy(), ids[lo:hi]) and np.array_equal(got[1].numpy(), lengths[lo:hi])
-    assert np.array_equal(got[2].numpy(), sid[lo:hi])
-    # stand-in synthesiser: utterance b -> lengths[b]*4 samples of value ids[b,0]
-    pcm, offs = [], [0]
-    for i in range(hi - lo):
-        n = int(got[1][i]) * 4
-        pcm.append(np.full(n, int(got[0][i, 0]), dtype=np.int16))
-        offs.append(offs[-1] + n)
-    out = gather_pcm(torch.from_numpy(np.concatenate(pcm)), offs, "cpu")
+    scatter = IdScatter(max_rows=9, max_t=16, device="cpu", payload_group=pg, meta_group=mg)
+    per = (9 + world - 1) // world
+    collector = PcmCollector(capacity_samples=per * 16 * 4, max_rows_per_rank=per, device="cpu", payload_group=pg,
+                             meta_group=mg, depth=2)
+    tickets, want = [], []
+    for step in range(5):      # more steps than slots: buffers are reused, nothing is allocated per step
+        rng = np.random.default_rng(step)
+        Bs = B if step != 3 else 2          # a batch smaller than the world still works (rank 1 gets 1 row or none)
+        Bs = 1 if step == 4 else Bs
+        ids = rng.integers(4, 50, size=(Bs, T)).astype(np.int64)
+        lengths = rng.integers(1, T + 1, size=Bs).astype(np.int64)
+        sid = (np.arange(Bs) % 3).astype(np.int64) if step % 2 == 0 else None
+        got = scatter(ids if rank == 0 else None, lengths if rank == 0 else None, sid if rank == 0 else None)
+        lo, hi = shard_bounds(Bs, world, rank)
+        assert got[0].shape == (hi - lo, 16)
+        assert np.array_equal(got[0][:, :T].numpy(), ids[lo:hi]) and not got[0][:, T:].any()
+        assert np.array_equal(got[1], lengths[lo:hi])
+        assert (got[2] is None) if sid is None else np.array_equal(got[2], sid[lo:hi])
+        # stand-in synthesiser: utterance b -> lengths[b] frames of 4 samples, every sample = ids[b,0] + step
+        buf = collector.send_buffer()
+        n, frames = 0, []
+        for i in range(hi - lo):
+            k = int(got[1][i]) * 4
+            buf[n:n + k] = int(got[0][i, 0]) + step
+            n += k
+            frames.append(int(got[1][i]))
+        tickets.append(collector.submit(n, frames))
+        want.append((ids, lengths, step))
+        if len(tickets) == 2:                  # collect one step behind, like the bench's pipelined loop
+            _check(collector.collect(tickets.pop(0)), want.pop(0), rank, world)
+    while tickets:
+        _check(collector.collect(tickets.pop(0)), want.pop(0), rank, world)
+    collector.drain()
     if rank == 0:
-        bufs, offsets = out
-        flat = []
-        for r in range(world):
-            for i in range(len(offsets[r]) - 1):
-                flat.append(bufs[r][offsets[r][i]:offsets[r][i + 1]].numpy())
-        assert len(flat) == B
-        for b in range(B):
-            assert flat[b].shape[0] == lengths[b] * 4 and (flat[b] == ids[b, 0]).all()
         Path(tmp, "ok").write_text("ok")
-    else:
-        assert out is None
     dist.destroy_process_group()
+
+
+def _check(out, want, rank, world):
+    ids, lengths, step = want
+    if rank != 0:
+        assert out is None
+        return
+    pcm, frames = out
+    assert len(frames) == world
+    flat = np.concatenate([np.asarray(f) for f in frames])
+    assert np.array_equal(flat, lengths)                      # rank order == row order
+    assert pcm.dtype == np.int16 and pcm.shape[0] == int(lengths.sum()) * 4
+    off = 0
+    for b in range(len(lengths)):
+        k = int(lengths[b]) * 4
+        assert (pcm[off:off + k] == ids[b, 0] + step).all()
+        off += k
 
 
 def test_scatter_gather_world2_gloo(tmp_path):
     import torch.multiprocessing as mp
     port = 29500 + (os.getpid() % 2000)
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "ok").exists()
+
+
+def test_scatter_gather_world3_gloo(tmp_path):
+    import torch.multiprocessing as mp
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(3, port, str(tmp_path)), nprocs=3, join=True)
     assert (tmp_path / "ok").exists()
