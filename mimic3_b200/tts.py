@@ -29,38 +29,43 @@ PHONEMES_LIST_TYPE = typing.List[typing.List[str]]
 DEFAULT_VOICE = "en_UK/apope_low"   # mimic3_tts/const.py:20
 
 
-@dataclass
-class BaseResult:
-    """opentts_abc.BaseResult (``opentts_abc/__init__.py:84-93``)."""
+try:
+    # The plugin surface's own result types (``opentts_abc/__init__.py:84-141``, stdlib only; installed with Mimic 3):
+    # the HTTP server dispatches on ``isinstance(result, AudioResult)`` (``mimic3_http/synthesis.py:60-85``), so the
+    # queue must hand out THESE classes wherever the reference is installed.
+    from opentts_abc import AudioResult, BaseResult, MarkResult
+except ImportError:  # stand-alone use without Mimic 3 on the path: structurally identical local definitions
 
-    tag: typing.Optional[typing.Any] = None
+    @dataclass
+    class BaseResult:
+        """opentts_abc.BaseResult (``opentts_abc/__init__.py:84-93``)."""
 
+        tag: typing.Optional[typing.Any] = None
 
-@dataclass
-class AudioResult(BaseResult):
-    """opentts_abc.AudioResult (``opentts_abc/__init__.py:96-127``): raw 16-bit mono audio of one sentence or break."""
+    @dataclass
+    class AudioResult(BaseResult):
+        """opentts_abc.AudioResult (``opentts_abc/__init__.py:96-127``): raw 16-bit mono audio of one sentence or break."""
 
-    sample_rate_hz: int = 22050
-    sample_width_bytes: int = 2
-    num_channels: int = 1
-    audio_bytes: bytes = b""
+        sample_rate_hz: int = 22050
+        sample_width_bytes: int = 2
+        num_channels: int = 1
+        audio_bytes: bytes = b""
 
-    def to_wav_bytes(self) -> bytes:
-        with io.BytesIO() as wav_io:
-            wav_file: wave.Wave_write = wave.open(wav_io, "wb")
-            with wav_file:
-                wav_file.setframerate(self.sample_rate_hz)
-                wav_file.setsampwidth(self.sample_width_bytes)
-                wav_file.setnchannels(self.num_channels)
-                wav_file.writeframes(self.audio_bytes)
-            return wav_io.getvalue()
+        def to_wav_bytes(self) -> bytes:
+            with io.BytesIO() as wav_io:
+                wav_file: wave.Wave_write = wave.open(wav_io, "wb")
+                with wav_file:
+                    wav_file.setframerate(self.sample_rate_hz)
+                    wav_file.setsampwidth(self.sample_width_bytes)
+                    wav_file.setnchannels(self.num_channels)
+                    wav_file.writeframes(self.audio_bytes)
+                return wav_io.getvalue()
 
+    @dataclass
+    class MarkResult(BaseResult):
+        """opentts_abc.MarkResult (``opentts_abc/__init__.py:130-141``): an SSML <mark> was reached."""
 
-@dataclass
-class MarkResult(BaseResult):
-    """opentts_abc.MarkResult (``opentts_abc/__init__.py:130-141``): an SSML <mark> was reached."""
-
-    name: str = ""
+        name: str = ""
 
 
 @dataclass

@@ -8,6 +8,11 @@ import pytest
 ROOT = Path(__file__).resolve().parent.parent
 if str(ROOT) not in sys.path:
     sys.path.insert(0, str(ROOT))
+# the unmodified reference package (mimic3_tts, opentts_abc), installed with --no-deps into baseline/_ref:
+# on the path from the start so that `opentts_abc` resolves to the reference's own module everywhere
+_REF = ROOT / "baseline" / "_ref"
+if (_REF / "opentts_abc").is_dir() and str(_REF) not in sys.path:
+    sys.path.append(str(_REF))
 
 
 def pytest_configure(config):

@@ -31,7 +31,8 @@ def test_plan_sentences_matches_reference_end_utterance():
                 queue.append(tts.B200Phonemes(current_settings=_settings(q["settings"]), phonemes=q["phonemes"],
                                               is_utterance=q["is_utterance"]))
             elif q["kind"] == "break":
-                queue.append(tts.AudioResult(sample_rate_hz=22050, audio_bytes=bytes(int(q["ms"] / 1000.0 * 22050) * 2)))
+                queue.append(tts.AudioResult(sample_rate_hz=22050, sample_width_bytes=2, num_channels=1,
+                                                 audio_bytes=bytes(int(q["ms"] / 1000.0 * 22050) * 2)))
             else:
                 queue.append(tts.MarkResult(name=q["name"]))
         plan = tts.plan_sentences(queue)
