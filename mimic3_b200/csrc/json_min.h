@@ -23,6 +23,13 @@ struct JsonValue {
     auto it = obj.find(k);
     return it == obj.end() ? nullptr : &it->second;
   }
+  // number_or() narrowed to int with a range check: NaN / huge doubles are an error, not undefined behaviour
+  int int_or(const std::string& k, int d) const {
+    const double v = number_or(k, double(d));
+    if (!(v >= -2147483648.0 && v <= 2147483647.0))
+      throw std::runtime_error("config.json: \"" + k + "\" is not a representable integer");
+    return int(v);
+  }
   double number_or(const std::string& k, double d) const {
     const JsonValue* v = get(k);
     if (!v) return d;
@@ -57,6 +64,15 @@ class JsonParser {
  private:
   const std::string& s_;
   size_t p_ = 0;
+  int depth_ = 0;
+  static constexpr int kMaxDepth = 64;  // config.json nests 3 deep; bounded recursion = no stack overflow on "[[[[..."
+  struct Nest {
+    JsonParser& p;
+    explicit Nest(JsonParser& q) : p(q) {
+      if (++p.depth_ > kMaxDepth) p.fail("nesting too deep");
+    }
+    ~Nest() { --p.depth_; }
+  };
   [[noreturn]] void fail(const char* m) const {
     throw std::runtime_error(std::string("config.json: ") + m + " at byte " + std::to_string(p_));
   }
@@ -72,6 +88,7 @@ class JsonParser {
     return false;
   }
   JsonValue value() {
+    Nest nest(*this);
     ws();
     if (p_ >= s_.size()) fail("unexpected end");
     JsonValue v;

@@ -16,9 +16,13 @@ struct OnnxTensor {
   std::vector<int64_t> dims;
   std::vector<float> f32;    // populated for FLOAT
   std::vector<int64_t> i64;  // populated for INT64
+  // element count; negative dims or a product beyond 2^40 (no voice comes near) -> -1, which no caller accepts
   int64_t numel() const {
     int64_t n = 1;
-    for (auto d : dims) n *= d;
+    for (auto d : dims) {
+      if (d < 0 || (d > 0 && n > (int64_t(1) << 40) / d)) return -1;
+      n *= d;
+    }
     return n;
   }
 };

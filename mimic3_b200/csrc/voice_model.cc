@@ -29,7 +29,11 @@ std::string read_file(const std::string& p) {
 std::vector<int> int_list(const JsonValue* v, const std::vector<int>& dflt) {
   if (!v || v->type != JsonValue::Array) return dflt;
   std::vector<int> out;
-  for (auto& e : v->arr) out.push_back(int(e.num));
+  for (auto& e : v->arr) {
+    if (e.type != JsonValue::Number || !(e.num >= -2147483648.0 && e.num <= 2147483647.0))
+      throw std::runtime_error("config.json: integer list holds a non-integer");
+    out.push_back(int(e.num));
+  }
   return out;
 }
 
@@ -76,14 +80,14 @@ HostVoice load_host_voice(const std::string& path) {
     JsonValue root = JsonParser(text).parse();
     VoiceConfig& c = hv.cfg;
     if (const JsonValue* m = root.get("model")) {
-      c.num_symbols = int(m->number_or("num_symbols", 0));
-      c.n_speakers = int(m->number_or("n_speakers", 1));
-      c.inter = int(m->number_or("inter_channels", 192));
-      c.hidden = int(m->number_or("hidden_channels", 192));
-      c.filter = int(m->number_or("filter_channels", 768));
-      c.n_heads = int(m->number_or("n_heads", 2));
-      c.n_layers = int(m->number_or("n_layers", 6));
-      c.kernel_size = int(m->number_or("kernel_size", 3));
+      c.num_symbols = m->int_or("num_symbols", 0);
+      c.n_speakers = m->int_or("n_speakers", 1);
+      c.inter = m->int_or("inter_channels", 192);
+      c.hidden = m->int_or("hidden_channels", 192);
+      c.filter = m->int_or("filter_channels", 768);
+      c.n_heads = m->int_or("n_heads", 2);
+      c.n_layers = m->int_or("n_layers", 6);
+      c.kernel_size = m->int_or("kernel_size", 3);
       c.resblock = m->string_or("resblock", "1");
       c.rb_kernels = int_list(m->get("resblock_kernel_sizes"), c.rb_kernels);
       if (const JsonValue* d = m->get("resblock_dilation_sizes"); d && d->type == JsonValue::Array) {
@@ -92,15 +96,15 @@ HostVoice load_host_voice(const std::string& path) {
       }
       c.up_rates = int_list(m->get("upsample_rates"), c.up_rates);
       c.up_kernels = int_list(m->get("upsample_kernel_sizes"), c.up_kernels);
-      c.up_init = int(m->number_or("upsample_initial_channel", 512));
-      c.gin = int(m->number_or("gin_channels", 0));
+      c.up_init = m->int_or("upsample_initial_channel", 512);
+      c.gin = m->int_or("gin_channels", 0);
       c.use_sdp = m->number_or("use_sdp", 1) != 0;
     } else {
       throw std::runtime_error("config.json: no \"model\" section");
     }
     if (const JsonValue* a = root.get("audio")) {
-      c.sample_rate = int(a->number_or("sample_rate", 22050));
-      c.hop_length = int(a->number_or("hop_length", 256));
+      c.sample_rate = a->int_or("sample_rate", 22050);
+      c.hop_length = a->int_or("hop_length", 256);
     }
     if (const JsonValue* i = root.get("inference")) {
       c.length_scale = float(i->number_or("length_scale", 1.0));
@@ -115,7 +119,45 @@ HostVoice load_host_voice(const std::string& path) {
       throw std::runtime_error("config.json: resblock_kernel_sizes / resblock_dilation_sizes length mismatch");
     if (c.up_rates.size() != c.up_kernels.size())
       throw std::runtime_error("config.json: upsample_rates / upsample_kernel_sizes length mismatch");
+    // ranges BEFORE any arithmetic on them: a crafted config must come back as M3_ERR_MODEL, never as SIGFPE / bad_alloc
+    auto in_range = [](const char* what, long long v, long long lo, long long hi) {
+      if (v < lo || v > hi)
+        throw std::runtime_error(std::string("config.json: ") + what + " = " + std::to_string(v) + " outside [" +
+                                 std::to_string(lo) + ", " + std::to_string(hi) + "]");
+    };
+    in_range("model.num_symbols", c.num_symbols, 0, 1 << 20);
+    in_range("model.n_speakers", c.n_speakers, 0, 1 << 20);
+    in_range("model.inter_channels", c.inter, 2, 4096);
+    in_range("model.hidden_channels", c.hidden, 1, 4096);
+    in_range("model.filter_channels", c.filter, 1, 16384);
+    in_range("model.n_heads", c.n_heads, 1, 64);
+    in_range("model.n_layers", c.n_layers, 1, 64);
+    in_range("model.kernel_size", c.kernel_size, 1, 15);
+    in_range("model.upsample_initial_channel", c.up_init, 2, 4096);
+    in_range("model.gin_channels", c.gin, 0, 8192);
+    in_range("audio.sample_rate", c.sample_rate, 1, 768000);
+    in_range("audio.hop_length", c.hop_length, 1, 1 << 16);
+    in_range("model.upsample_rates (count)", (long long)c.up_rates.size(), 1, 8);
+    in_range("model.resblock_kernel_sizes (count)", (long long)c.rb_kernels.size(), 1, 8);
+    long long hop = 1;
+    for (size_t i = 0; i < c.up_rates.size(); ++i) {
+      in_range("model.upsample_rates[i]", c.up_rates[i], 1, 64);
+      in_range("model.upsample_kernel_sizes[i]", c.up_kernels[i], 1, 256);
+      hop *= c.up_rates[i];
+    }
+    in_range("product of model.upsample_rates", hop, 1, 1 << 16);
+    if ((c.up_init >> c.up_rates.size()) < 1)
+      throw std::runtime_error("config.json: upsample_initial_channel too small for the number of upsample stages");
+    for (size_t j = 0; j < c.rb_kernels.size(); ++j) {
+      in_range("model.resblock_kernel_sizes[j]", c.rb_kernels[j], 1, 31);
+      if (!(c.rb_kernels[j] & 1)) throw std::runtime_error("config.json: resblock kernel sizes must be odd");
+      in_range("model.resblock_dilation_sizes[j] (count)", (long long)c.rb_dils[j].size(), 1, 8);
+      for (int d : c.rb_dils[j]) in_range("model.resblock_dilation_sizes[j][d]", d, 1, 256);
+    }
+    if (c.inter & 1) throw std::runtime_error("config.json: inter_channels must be even (coupling layers split it)");
     if (c.hidden % c.n_heads) throw std::runtime_error("config.json: hidden_channels not divisible by n_heads");
+    if (!std::isfinite(c.length_scale) || !std::isfinite(c.noise_scale) || !std::isfinite(c.noise_w))
+      throw std::runtime_error("config.json: inference scales must be finite");
   }
 
   // ---- generator.onnx -> named parameters
@@ -133,7 +175,7 @@ HostVoice load_host_voice(const std::string& path) {
     if (vit == hv.params.end()) continue;
     const OnnxTensor& g = hv.params[gn];
     const OnnxTensor& v = vit->second;
-    if (v.dims.empty() || g.numel() != v.dims[0]) continue;
+    if (v.dims.empty() || v.dims[0] <= 0 || v.numel() <= 0 || g.numel() != v.dims[0]) continue;
     OnnxTensor w = v;
     w.name = base + ".weight";
     int64_t inner = v.numel() / v.dims[0];

@@ -133,7 +133,7 @@ class InferenceResult:
     until ``close()`` (which turns them into copies and returns the buffers to the engine's pool)."""
 
     __slots__ = ("pcm", "audio", "stream", "sample_offsets", "frames", "peaks", "device_ms", "launches",
-                 "tensors", "device_pcm_ptr", "hop_length", "_lib", "_res")
+                 "tensors", "device_pcm_ptr", "hop_length", "_lib", "_res", "_session")
 
     def detach(self):
         """Turn the views into owned copies and release the engine buffers."""
@@ -195,6 +195,8 @@ class B200Session:
         self.device = int(info.device)
 
     def close(self):
+        """Frees the voice (weights, contexts, pinned buffers).  Results obtained with ``copy=False`` must be closed
+        or detached first: their views point into those buffers."""
         if getattr(self, "_h", None):
             self._lib.m3_voice_free(self._h)
             self._h = None
@@ -283,45 +285,45 @@ class B200Session:
             _raise(self._lib, rc)
         out = InferenceResult()
         out._lib, out._res = self._lib, res
+        out._session = self   # zero-copy views point into buffers the voice owns: keep it alive as long as the result
         out.hop_length = int(self.info.hop_length)
         out.stream = None
-        if True:
-            off = np.ctypeslib.as_array(self._lib.m3_result_sample_offsets(res), (batch + 1,)).copy()
-            out.sample_offsets = off
-            out.frames = np.ctypeslib.as_array(self._lib.m3_result_num_frames(res), (batch,)).copy()
-            out.peaks = np.ctypeslib.as_array(self._lib.m3_result_peaks(res), (batch,)).copy()
-            total = int(off[-1])
-            out.pcm = out.audio = None
-            if host_copy:
-                out.pcm = np.ctypeslib.as_array(self._lib.m3_result_pcm(res), (max(total, 1),))[:total]
-                nbytes = C.c_int64()
-                sp = self._lib.m3_result_stream(res, C.byref(nbytes))
-                if nbytes.value:
-                    out.stream = np.ctypeslib.as_array(sp, (nbytes.value,))
-                if keep_float:
-                    out.audio = np.ctypeslib.as_array(self._lib.m3_result_audio(res), (max(total, 1),))[:total]
-            out.device_ms = float(self._lib.m3_result_device_ms(res))
-            out.launches = int(self._lib.m3_result_kernel_launches(res))
-            out.device_pcm_ptr = self._lib.m3_result_device_pcm(res)
-            if device_pcm_out is not None and total:
-                import torch
+        off = np.ctypeslib.as_array(self._lib.m3_result_sample_offsets(res), (batch + 1,)).copy()
+        out.sample_offsets = off
+        out.frames = np.ctypeslib.as_array(self._lib.m3_result_num_frames(res), (batch,)).copy()
+        out.peaks = np.ctypeslib.as_array(self._lib.m3_result_peaks(res), (batch,)).copy()
+        total = int(off[-1])
+        out.pcm = out.audio = None
+        if host_copy:
+            out.pcm = np.ctypeslib.as_array(self._lib.m3_result_pcm(res), (max(total, 1),))[:total]
+            nbytes = C.c_int64()
+            sp = self._lib.m3_result_stream(res, C.byref(nbytes))
+            if nbytes.value:
+                out.stream = np.ctypeslib.as_array(sp, (nbytes.value,))
+            if keep_float:
+                out.audio = np.ctypeslib.as_array(self._lib.m3_result_audio(res), (max(total, 1),))[:total]
+        out.device_ms = float(self._lib.m3_result_device_ms(res))
+        out.launches = int(self._lib.m3_result_kernel_launches(res))
+        out.device_pcm_ptr = self._lib.m3_result_device_pcm(res)
+        if device_pcm_out is not None and total:
+            import torch
 
-                class _View:  # zero-copy view of the engine's device buffer
-                    __cuda_array_interface__ = {"shape": (total,), "typestr": "<i2",
-                                                "data": (int(out.device_pcm_ptr), False), "version": 2}
-                device_pcm_out[:total].copy_(torch.as_tensor(_View(), device=device_pcm_out.device))
-                torch.cuda.current_stream(device_pcm_out.device).synchronize()
-            out.tensors = {}
-            for name in debug_tensors:
-                data = C.POINTER(C.c_float)()
-                rows, cols = C.c_int64(), C.c_int64()
-                rc = self._lib.m3_result_tensor(res, name.encode(), C.byref(data), C.byref(rows), C.byref(cols))
-                if rc == M3_OK:
-                    n = rows.value * cols.value
-                    out.tensors[name] = np.ctypeslib.as_array(data, (max(n, 1),))[:n].copy().reshape(rows.value, cols.value)
-            if copy or not host_copy:
-                out.detach()  # owned copies (or nothing on the host): give the context back immediately
-            return out
+            class _View:  # zero-copy view of the engine's device buffer
+                __cuda_array_interface__ = {"shape": (total,), "typestr": "<i2",
+                                            "data": (int(out.device_pcm_ptr), False), "version": 2}
+            device_pcm_out[:total].copy_(torch.as_tensor(_View(), device=device_pcm_out.device))
+            torch.cuda.current_stream(device_pcm_out.device).synchronize()
+        out.tensors = {}
+        for name in debug_tensors:
+            data = C.POINTER(C.c_float)()
+            rows, cols = C.c_int64(), C.c_int64()
+            rc = self._lib.m3_result_tensor(res, name.encode(), C.byref(data), C.byref(rows), C.byref(cols))
+            if rc == M3_OK:
+                n = rows.value * cols.value
+                out.tensors[name] = np.ctypeslib.as_array(data, (max(n, 1),))[:n].copy().reshape(rows.value, cols.value)
+        if copy or not host_copy:
+            out.detach()  # owned copies (or nothing on the host): give the context back immediately
+        return out
 
     # -- onnxruntime-compatible call (voice.py:230) ---------------------------------------
     def run(self, output_names, input_feed: Dict[str, np.ndarray], run_options=None) -> List[np.ndarray]:

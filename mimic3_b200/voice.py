@@ -15,6 +15,7 @@ from __future__ import annotations
 import csv
 import json
 import logging
+import sys
 import threading
 import time
 import typing
@@ -24,9 +25,21 @@ from types import SimpleNamespace
 import numpy as np
 
 from .engine import B200Session
-from .phonemes import load_phoneme_ids, load_phoneme_map, phonemes2ids
 
 _LOGGER = logging.getLogger(__name__)
+
+try:
+    # the package the reference itself calls (voice.py:33, 133-152, 268-271, 302-307): whenever it is installed it
+    # is the id conversion, so ids -- and audio -- are the reference's by construction
+    from phonemes2ids import load_phoneme_ids, load_phoneme_map, phonemes2ids
+    if getattr(sys.modules.get("phonemes2ids"), "__name__", "") == "mimic3_b200.phonemes":
+        raise ImportError  # a test registered the restatement under that name
+    PHONEMES2IDS_SOURCE = "phonemes2ids"
+except ImportError:
+    from .phonemes import load_phoneme_ids, load_phoneme_map, phonemes2ids
+    PHONEMES2IDS_SOURCE = "mimic3_b200.phonemes"
+    _LOGGER.warning("phonemes2ids is not installed: using the in-repo restatement (mimic3_b200.phonemes; parity with "
+                    "the package is pinned by its documented behaviour only)")
 
 DEFAULT_RATE = 1.0
 DEFAULT_VOLUME = 100.0   # mimic3_tts/const.py
@@ -84,8 +97,8 @@ class B200Voice:
         self.phoneme_to_id = phoneme_to_id
         self.phoneme_map = phoneme_map
         self.speaker_map = speaker_map
-        # any callable with the phonemes2ids.phonemes2ids keyword signature (voice.py:133-152); default:
-        # the restatement in mimic3_b200.phonemes
+        # any callable with the phonemes2ids.phonemes2ids keyword signature (voice.py:133-152); default: the real
+        # phonemes2ids package when it is installed, else the restatement in mimic3_b200.phonemes (module top)
         self.phonemes_to_ids_fn = phonemes_to_ids_fn or phonemes2ids
 
     # -- voice.py:126-152 ---------------------------------------------------------------

@@ -52,5 +52,57 @@ for it in range(max(10, N // 4)):
     codes[rc] = codes.get(rc, 0) + 1
     if rc == 0:
         lib.m3_voice_free(h)
+# semantic corruption: fields that are well-formed JSON / protobuf but out of range -- zeros, negatives, huge
+# values, NaN -- must come back as error codes too (n_heads = 0 used to be a SIGFPE, deep nesting a stack overflow)
+import json
+base_cfg = json.loads(cfg_good)
+sem = 0
+for key in ("n_heads", "n_layers", "hidden_channels", "inter_channels", "filter_channels", "kernel_size",
+            "upsample_initial_channel", "num_symbols", "n_speakers", "gin_channels"):
+    for val in (0, -1, -2 ** 31, 2 ** 31 - 1, 1e300, float("nan"), 3.7, "x", None, [1], True):
+        c = json.loads(cfg_good)
+        c["model"][key] = val
+        (d / "v" / "config.json").write_text(json.dumps(c))
+        h = C.c_void_p()
+        rc = lib.m3_voice_load(str(d / "v").encode(), 0, C.byref(h))
+        codes[rc] = codes.get(rc, 0) + 1
+        sem += 1
+        if rc == 0:
+            lib.m3_voice_free(h)
+for key, vals in (("upsample_rates", ([0, 1], [-4, 4], [], [1e9, 2], [2] * 40, ["a"])),
+                  ("upsample_kernel_sizes", ([0, 0], [-3, 4], [10 ** 9, 4])),
+                  ("resblock_kernel_sizes", ([0, 0], [2, 4], [-3, 5], [])),
+                  ("resblock_dilation_sizes", ([[0], [0]], [[-1, 2], [2, 6]], [[], []], [[10 ** 9], [1]]))):
+    for val in vals:
+        c = json.loads(cfg_good)
+        c["model"][key] = val
+        (d / "v" / "config.json").write_text(json.dumps(c))
+        h = C.c_void_p()
+        rc = lib.m3_voice_load(str(d / "v").encode(), 0, C.byref(h))
+        codes[rc] = codes.get(rc, 0) + 1
+        sem += 1
+        if rc == 0:
+            lib.m3_voice_free(h)
+for doc in ("[" * 2_000_000, "{\"a\":" * 500_000, '{"model": ' + "[" * 100_000 + "]" * 100_000 + "}"):
+    (d / "v" / "config.json").write_text(doc)
+    h = C.c_void_p()
+    rc = lib.m3_voice_load(str(d / "v").encode(), 0, C.byref(h))
+    assert rc != 0
+    codes[rc] = codes.get(rc, 0) + 1
+    sem += 1
+# weight_g / weight_v pairs with an empty leading dimension (division by dims[0] in the fusion)
+(d / "v" / "config.json").write_bytes(cfg_good)
+from mimic3_b200 import onnx_writer as ow
+params = sv.make_params(sv.tiny_config(n_speakers=2), 1)
+inits = [ow.tensor_proto(k, v) for k, v in params.items() if not k.startswith("flow.flows.0.enc.in_layers.0.weight")]
+inits.append(ow.tensor_proto("flow.flows.0.enc.in_layers.0.weight_g", np.zeros((0,), np.float32)))
+inits.append(ow.tensor_proto("flow.flows.0.enc.in_layers.0.weight_v", np.zeros((0, 4, 5), np.float32)))
+(d / "v" / "generator.onnx").write_bytes(ow.model_proto([], inits, [], []))
+h = C.c_void_p()
+rc = lib.m3_voice_load(str(d / "v").encode(), 0, C.byref(h))
+assert rc != 0, "a voice whose in_layers weight is empty must not load"
+codes[rc] = codes.get(rc, 0) + 1
+sem += 1
+print("semantic cases:", sem)
 print("return codes:", codes)
 shutil.rmtree(d)
