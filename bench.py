@@ -415,6 +415,7 @@ def main():
         cap = per * max_t * 12 * 256
         coll = PcmCollector(cap, per, dev, payload_group=gather_pg, meta_group=meta_pg, depth=max(1, args.e2e_depth))
     tickets = deque()
+    trace = {"scatter": 0.0, "infer": 0.0, "submit": 0.0, "collect": 0.0, "n": 0} if os.environ.get("M3B200_BENCH_TRACE") else None
 
     def e2e_collect(t):
         got = coll.collect(t)
@@ -435,17 +436,29 @@ def main():
                 assert r.pcm.shape[0] == r.total_samples
                 r.close()
                 continue
+            ta = time.perf_counter()
             d_ids, lens, sids = scat(j["ids"] if rank == 0 else None, j["lengths"] if rank == 0 else None,
                                      j["sid"] if rank == 0 else None)
             buf = coll.send_buffer()
+            tb = time.perf_counter()
             if len(lens):
                 r = j["sess"].infer(d_ids.stride(0), lens, j["scales"], sids, seed=seed, host_copy=False,
                                     device_ids_ptr=d_ids.data_ptr(), device_pcm_out=buf)
+                tc_ = time.perf_counter()
                 tickets.append(coll.submit(r.total_samples, r.frames))
             else:
+                tc_ = time.perf_counter()
                 tickets.append(coll.submit(0, []))
+            td = time.perf_counter()
             while len(tickets) >= max(1, args.e2e_depth):
                 n += e2e_collect(tickets.popleft())
+            if trace is not None:
+                te = time.perf_counter()
+                trace["scatter"] += tb - ta
+                trace["infer"] += tc_ - tb
+                trace["submit"] += td - tc_
+                trace["collect"] += te - td
+                trace["n"] += 1
         return n
 
     def e2e_drain():
@@ -508,6 +521,9 @@ def main():
     e2e_samples += e2e_drain()
     sync_all()
     e2e_wall = time.perf_counter() - t1
+    if trace is not None and trace["n"]:
+        log(f"[bench trace] rank {rank}: per engine call (ms): " + ", ".join(
+            f"{k} {trace[k] / trace['n'] * 1e3:.3f}" for k in ("scatter", "infer", "submit", "collect")))
 
     # ---- reduce over ranks: max time, summed samples ------------------------------------------------
     vec = torch.tensor([wall, dev_ms / 1e3, e2e_wall], dtype=torch.float64, device="cuda")
