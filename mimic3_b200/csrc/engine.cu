@@ -1545,7 +1545,9 @@ Result* run_inference(Voice& v, const int64_t* ids, const int64_t* lengths, int 
       mp.HX = ms.HX;
       mp.HY = ms.HY;
       mp.inv_nk = 1.0f / float(ms.nk);
-      if (!getenv("M3B200_MRF_V1") && mrf_ws_supported(mp, u.cout)) launch_mrf_ws(mp, dv.tc_fmt, batch, Fmax, st);
+      const bool v1 = getenv("M3B200_MRF_V1") != nullptr;  // per-window kernel for every stage (A/B, parity tests)
+      if (!v1 && mrf_ws_supported(mp, u.cout)) launch_mrf_ws(mp, dv.tc_fmt, batch, Fmax, st);
+      else if (!v1 && mrf_ws128_supported(mp, u.cout)) launch_mrf_ws128(mp, dv.tc_fmt, batch, Fmax, st);
       else launch_mrf_tc(mp, u.cout, dv.tc_fmt, batch, Fmax, st);
     } else
     for (int j = 0; j < nk; ++j) {

@@ -230,6 +230,10 @@ bool mrf_tc_supported(int C, int nk, int nd, const int* k, int max_halo);
 // persistent warp-specialised variant for C = 64, three ResBlock2 chains (kernels_tc_mrf2.cu)
 bool mrf_ws_supported(const MrfParams& p, int C);
 void launch_mrf_ws(const MrfParams& p, int fmt, int n_seg, int max_len, cudaStream_t st);
+// C = 128 stage, persistent + warp-specialised (kernels_tc_mrf3.cu): chains serialised through one TMEM tile pair,
+// running sum in TMEM, 16 KB half-tap weight ring.
+bool mrf_ws128_supported(const MrfParams& p, int C);
+void launch_mrf_ws128(const MrfParams& p, int fmt, int n_seg, int max_len, cudaStream_t st);
 // fmt: 0 = fp16 operands, 1 = bf16 operands
 void launch_mrf_tc(const MrfParams& p, int C, int fmt, int n_seg, int max_len, cudaStream_t st);
 
