@@ -62,6 +62,44 @@ int32_t m3_device_count(void);
  * (mimic3_tts/voice.py:378-407).  `path` is the voice directory (config.json,
  * generator.onnx -- voice.py:261,273) or the generator.onnx inside it. */
 int32_t m3_voice_load(const char* path, int32_t device, m3_voice** out);
+
+/* Packed-weight cache.  The reference parses + optimises generator.onnx once per path per
+ * process (voice.py:277-299, 378-407) and checks voice files against the sha256_sum entries of
+ * mimic3_tts/voices.json (mimic3_tts/_resources.py:35-51, download.py:108-117).  Here the one-time conversion of
+ * generator.onnx into the engine's packed operand slabs is kept as <cache_dir>/<key>.m3w and re-read on later loads;
+ * the blob records the sha256 of the generator.onnx it was made from, so the manifest check is a string compare.
+ * Zero-initialise, then set struct_size = sizeof(m3_load_opts). */
+#define M3_LOAD_VERIFY_SHA256 1u  /* re-hash generator.onnx on a cache hit too (otherwise the recorded digest is used) */
+#define M3_LOAD_NO_CACHE_WRITE 2u /* read an existing blob but never write one                                        */
+typedef struct m3_load_opts {
+  uint32_t struct_size;
+  uint32_t flags;               /* M3_LOAD_*                                                                          */
+  const char* cache_dir;        /* directory of *.m3w blobs; NULL: $M3B200_WEIGHT_CACHE, unset/empty = no cache       */
+  const char* expected_sha256;  /* voices.json "sha256_sum" of generator.onnx (64 hex digits) or NULL: a mismatch is
+                                   M3_ERR_MODEL, like a failed download check                                          */
+} m3_load_opts;
+typedef struct m3_load_stats {
+  int32_t from_cache;     /* 1: slabs came from a cache blob                          */
+  int32_t cache_written;  /* 1: this load wrote the blob                              */
+  double parse_ms;        /* config.json + generator.onnx -> named fp32 parameters    */
+  double pack_ms;         /* bind + pack into GEMM-ready slabs                        */
+  double cache_read_ms;   /* read + validate the blob                                 */
+  double hash_ms;         /* sha256 passes over generator.onnx                        */
+  double upload_ms;       /* cudaMalloc + host->device copies                         */
+  double total_ms;
+  char onnx_sha256[65];   /* digest of generator.onnx ("" if never computed / recorded) */
+  char cache_file[512];   /* blob path ("" without a cache directory)                 */
+} m3_load_stats;
+int32_t m3_voice_load_ex(const char* path, int32_t device, const m3_load_opts* opts, m3_voice** out);
+int32_t m3_voice_load_stats(const m3_voice* voice, m3_load_stats* stats);
+/* GPU-free halves of the same thing: convert a voice into its blob (returns the blob path in out_file), validate a
+ * blob completely (header, checksum, every offset) and report the generator.onnx digest it records, hash a file the
+ * way mimic3_tts/utils.py file_sha256_sum does. */
+int32_t m3_weight_cache_build(const char* path, const char* cache_dir, const char* expected_sha256, char* out_file,
+                              int32_t out_cap);
+int32_t m3_weight_cache_check(const char* cache_file, char onnx_sha256_out[65]);
+int32_t m3_sha256_file(const char* path, char out[65]);
+
 void m3_voice_free(m3_voice* voice);
 int32_t m3_voice_get_info(const m3_voice* voice, m3_voice_info* info);
 

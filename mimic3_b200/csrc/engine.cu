@@ -249,11 +249,11 @@ struct Builder {
 
 }  // namespace
 
-std::unique_ptr<DeviceVoice> build_device_voice(const HostVoice& hv, int device) {
-  std::unique_ptr<DeviceVoice> dvp(new DeviceVoice());
-  DeviceVoice& dv = *dvp;
+PackedVoice pack_voice(const HostVoice& hv) {
+  PackedVoice pv;
+  pv.dv.reset(new DeviceVoice());
+  DeviceVoice& dv = *pv.dv;
   dv.cfg = hv.cfg;
-  dv.device = device;
   const VoiceConfig& c = hv.cfg;
   Builder B(hv);
   {
@@ -724,31 +724,63 @@ std::unique_ptr<DeviceVoice> build_device_voice(const HostVoice& hv, int device)
   }
   dv.cfg.gin = G;
 
-  // ---- upload (everything above is host-only, so model errors surface without a GPU)
-  {
-    int n = 0;
-    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
-      cudaGetLastError();
-      throw EngineError(M3_ERR_NOGPU, "no CUDA device visible: libm3b200 has no CPU fallback");
-    }
-    if (device < 0 || device >= n) throw EngineError(M3_ERR_INVALID, "device ordinal out of range");
-    int major = 0;
-    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device);
-    if (major != 10)
-      throw EngineError(M3_ERR_NOGPU, "device " + std::to_string(device) + " is compute capability " +
-                                          std::to_string(major) + ".x; this library carries sm_100a code only");
-  }
-  M3_CUDA(cudaSetDevice(device));
-  dv.slab_floats = B.pk.host.size();
-  M3_CUDA(cudaMalloc(&dv.slab, dv.slab_floats * sizeof(float)));
-  M3_CUDA(cudaMemcpy(dv.slab, B.pk.host.data(), dv.slab_floats * sizeof(float), cudaMemcpyHostToDevice));
-  for (auto& f : B.fix) *f.slot = dv.slab + f.off;
   dv.n_params = B.n_params;
-  if (!h16.empty()) {
-    M3_CUDA(cudaMalloc(&dv.slab16, h16.size() * sizeof(uint16_t)));
-    M3_CUDA(cudaMemcpy(dv.slab16, h16.data(), h16.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+  dv.slab_floats = B.pk.host.size();
+  pv.f32 = std::move(B.pk.host);
+  pv.h16 = std::move(B.h16);
+  pv.fix.reserve(B.fix.size());
+  for (auto& f : B.fix) pv.fix.emplace_back(f.slot, f.off);
+  pv.pack_flags = pack_flags_string();
+  return pv;
+}
+
+// Everything pack_voice reads from the environment (part of the weight-cache key: a blob packed under other
+// switches must not be picked up).
+std::string pack_flags_string() {
+  auto env = [](const char* n) {
+    const char* e = getenv(n);
+    return std::string(e ? e : "");
+  };
+  return "fmt=" + env("M3B200_TC_FORMAT") + ";simt=" + env("M3B200_FORCE_SIMT") + ";text_simt=" + env("M3B200_TEXT_SIMT") +
+         ";rows_nc=" + env("M3B200_ROWGEMM_NC");
+}
+
+void require_sm100(int device) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    throw EngineError(M3_ERR_NOGPU, "no CUDA device visible: libm3b200 has no CPU fallback");
   }
-  return dvp;
+  if (device < 0 || device >= n) throw EngineError(M3_ERR_INVALID, "device ordinal out of range");
+  int major = 0;
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device);
+  if (major != 10)
+    throw EngineError(M3_ERR_NOGPU, "device " + std::to_string(device) + " is compute capability " +
+                                        std::to_string(major) + ".x; this library carries sm_100a code only");
+}
+
+// Upload of the two slabs (everything before this is host-only, so model errors surface without a GPU).
+void upload_slabs(DeviceVoice& dv, int device, const float* f32, size_t n_f32, const uint16_t* h16, size_t n_h16) {
+  require_sm100(device);
+  M3_CUDA(cudaSetDevice(device));
+  dv.device = device;
+  dv.slab_floats = n_f32;
+  M3_CUDA(cudaMalloc(&dv.slab, std::max<size_t>(n_f32, 1) * sizeof(float)));
+  M3_CUDA(cudaMemcpy(dv.slab, f32, n_f32 * sizeof(float), cudaMemcpyHostToDevice));
+  if (n_h16) {
+    M3_CUDA(cudaMalloc(&dv.slab16, n_h16 * sizeof(uint16_t)));
+    M3_CUDA(cudaMemcpy(dv.slab16, h16, n_h16 * sizeof(uint16_t), cudaMemcpyHostToDevice));
+  }
+}
+
+std::unique_ptr<DeviceVoice> upload_voice(PackedVoice&& pv, int device) {
+  upload_slabs(*pv.dv, device, pv.f32.data(), pv.f32.size(), pv.h16.data(), pv.h16.size());
+  for (auto& f : pv.fix) *f.first = pv.dv->slab + f.second;
+  return std::move(pv.dv);
+}
+
+std::unique_ptr<DeviceVoice> build_device_voice(const HostVoice& hv, int device) {
+  return upload_voice(pack_voice(hv), device);
 }
 
 // ======================================================================================

@@ -154,6 +154,19 @@ struct DeviceVoice {
   ~DeviceVoice();
 };
 
+// Host-only result of binding + packing a voice: the DeviceVoice with every `const float*` slot still unresolved
+// (`fix` lists slot -> element offset into `f32`), the fp32 slab and the 16-bit tensor-core operand slab.
+struct PackedVoice {
+  std::unique_ptr<DeviceVoice> dv;
+  std::vector<float> f32;
+  std::vector<uint16_t> h16;
+  std::vector<std::pair<const float**, size_t>> fix;
+  std::string pack_flags;
+};
+PackedVoice pack_voice(const HostVoice& hv);                               // no CUDA call
+std::unique_ptr<DeviceVoice> upload_voice(PackedVoice&& pv, int device);   // M3_ERR_NOGPU without an sm_100 device
+void upload_slabs(DeviceVoice& dv, int device, const float* f32, size_t n_f32, const uint16_t* h16, size_t n_h16);
+std::string pack_flags_string();
 std::unique_ptr<DeviceVoice> build_device_voice(const HostVoice& hv, int device);
 
 struct Arena {

@@ -33,6 +33,7 @@ API_SYMBOLS = [
     "m3_result_device_pcm", "m3_result_device_ms", "m3_result_kernel_launches",
     "m3_result_tensor", "m3_result_free", "m3_selftest",
     "m3_infer_ex", "m3_result_stream", "m3_wav_header",
+    "m3_voice_load_ex", "m3_voice_load_stats", "m3_weight_cache_build", "m3_weight_cache_check", "m3_sha256_file",
 ]
 
 
@@ -60,6 +61,30 @@ class InferOpts(C.Structure):
     ]
 
 
+class LoadOpts(C.Structure):
+    """``m3_load_opts`` (include/m3b200.h)."""
+    _fields_ = [("struct_size", C.c_uint32), ("flags", C.c_uint32), ("cache_dir", C.c_char_p),
+                ("expected_sha256", C.c_char_p)]
+
+
+class LoadStats(C.Structure):
+    """``m3_load_stats`` (include/m3b200.h): where the load time of a voice went."""
+    _fields_ = [("from_cache", C.c_int32), ("cache_written", C.c_int32), ("parse_ms", C.c_double),
+                ("pack_ms", C.c_double), ("cache_read_ms", C.c_double), ("hash_ms", C.c_double),
+                ("upload_ms", C.c_double), ("total_ms", C.c_double), ("onnx_sha256", C.c_char * 65),
+                ("cache_file", C.c_char * 512)]
+
+    def as_dict(self) -> dict:
+        return {"from_cache": bool(self.from_cache), "cache_written": bool(self.cache_written),
+                "parse_ms": self.parse_ms, "pack_ms": self.pack_ms, "cache_read_ms": self.cache_read_ms,
+                "hash_ms": self.hash_ms, "upload_ms": self.upload_ms, "total_ms": self.total_ms,
+                "onnx_sha256": self.onnx_sha256.decode(), "cache_file": self.cache_file.decode()}
+
+
+LOAD_VERIFY_SHA256 = 1
+LOAD_NO_CACHE_WRITE = 2
+
+
 def library_path() -> Path:
     env = os.environ.get("M3B200_LIBRARY")
     return Path(env) if env else Path(__file__).resolve().parent / _LIB_NAME
@@ -83,6 +108,16 @@ def load_library() -> C.CDLL:
         lib.m3_device_count.restype = i32
         lib.m3_voice_load.restype = i32
         lib.m3_voice_load.argtypes = [C.c_char_p, i32, C.POINTER(vp)]
+        lib.m3_voice_load_ex.restype = i32
+        lib.m3_voice_load_ex.argtypes = [C.c_char_p, i32, C.POINTER(LoadOpts), C.POINTER(vp)]
+        lib.m3_voice_load_stats.restype = i32
+        lib.m3_voice_load_stats.argtypes = [vp, C.POINTER(LoadStats)]
+        lib.m3_weight_cache_build.restype = i32
+        lib.m3_weight_cache_build.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, i32]
+        lib.m3_weight_cache_check.restype = i32
+        lib.m3_weight_cache_check.argtypes = [C.c_char_p, C.c_char_p]
+        lib.m3_sha256_file.restype = i32
+        lib.m3_sha256_file.argtypes = [C.c_char_p, C.c_char_p]
         lib.m3_voice_free.restype = None
         lib.m3_voice_free.argtypes = [vp]
         lib.m3_voice_get_info.restype = i32
@@ -116,6 +151,37 @@ def load_library() -> C.CDLL:
         lib.m3_selftest.argtypes = [i32, C.POINTER(C.c_double)]
         _lib = lib
         return lib
+
+
+def weight_cache_build(voice_path, cache_dir, expected_sha256: Optional[str] = None) -> Path:
+    """One-time conversion of ``generator.onnx`` into the packed-weight blob, without a GPU (``m3_weight_cache_build``)."""
+    lib = load_library()
+    out = C.create_string_buffer(1024)
+    rc = lib.m3_weight_cache_build(str(voice_path).encode(), str(cache_dir).encode(),
+                                   expected_sha256.encode() if expected_sha256 else None, out, 1024)
+    if rc != M3_OK:
+        _raise(lib, rc)
+    return Path(out.value.decode())
+
+
+def weight_cache_check(cache_file) -> str:
+    """Validates a blob completely and returns the sha256 of the generator.onnx it was made from."""
+    lib = load_library()
+    out = C.create_string_buffer(65)
+    rc = lib.m3_weight_cache_check(str(cache_file).encode(), out)
+    if rc != M3_OK:
+        _raise(lib, rc)
+    return out.value.decode()
+
+
+def sha256_file(path) -> str:
+    """``m3_sha256_file``: what ``mimic3_tts.utils.file_sha256_sum`` computes."""
+    lib = load_library()
+    out = C.create_string_buffer(65)
+    rc = lib.m3_sha256_file(str(path).encode(), out)
+    if rc != M3_OK:
+        _raise(lib, rc)
+    return out.value.decode()
 
 
 def _raise(lib, code: int):
@@ -180,15 +246,28 @@ class InferenceResult:
 class B200Session:
     """Stands where ``onnxruntime.InferenceSession(generator.onnx)`` stands in Mimic 3."""
 
-    def __init__(self, path, sess_options=None, providers=None, device: Optional[int] = None):
+    def __init__(self, path, sess_options=None, providers=None, device: Optional[int] = None,
+                 cache_dir=None, expected_sha256: Optional[str] = None, verify_sha256: bool = False):
+        """``cache_dir``: directory of packed-weight blobs (``*.m3w``); ``None`` = ``$M3B200_WEIGHT_CACHE``, unset =
+        no cache.  ``expected_sha256``: the voice registry's ``sha256_sum`` of generator.onnx
+        (``mimic3_tts/voices.json``, checked by the reference's downloader, ``download.py:108-117``): a mismatch
+        raises.  ``verify_sha256`` re-hashes the file even on a cache hit."""
         self._lib = load_library()
         if device is None:
             device = int(os.environ.get("M3B200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
         handle = C.c_void_p()
-        rc = self._lib.m3_voice_load(str(path).encode(), int(device), C.byref(handle))
+        opts = LoadOpts()
+        opts.struct_size = C.sizeof(LoadOpts)
+        opts.flags = LOAD_VERIFY_SHA256 if verify_sha256 else 0
+        opts.cache_dir = str(cache_dir).encode() if cache_dir else None
+        opts.expected_sha256 = expected_sha256.encode() if expected_sha256 else None
+        rc = self._lib.m3_voice_load_ex(str(path).encode(), int(device), C.byref(opts), C.byref(handle))
         if rc != M3_OK:
             _raise(self._lib, rc)
         self._h = handle
+        st = LoadStats()
+        self._lib.m3_voice_load_stats(self._h, C.byref(st))
+        self.load_stats = st.as_dict()
         info = VoiceInfo()
         self._lib.m3_voice_get_info(self._h, C.byref(info))
         self.info = info

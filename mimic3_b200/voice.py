@@ -84,6 +84,22 @@ class VoiceConfig:
         return VoiceConfig(json.loads(config_file.read()))
 
 
+def registry_sha256(voice_dir, voices_registry, relative_path: str = "generator.onnx") -> typing.Optional[str]:
+    """``sha256_sum`` the reference's voice registry lists for a file of this voice, or None if the voice / file is not
+    listed.  ``voices_registry`` is ``mimic3_tts/voices.json`` as a path or the parsed dict
+    ``{"<lang>/<voice>": {"files": {"<relative path>": {"size_bytes", "sha256_sum"}}}}`` (``_resources.py:35-51``);
+    the voice key is the last two components of the voice directory (``voice_dir = voices_dir / voice_key``, ``download.py:86``)."""
+    if not isinstance(voices_registry, dict):
+        with open(voices_registry, "r", encoding="utf-8") as f:
+            voices_registry = json.load(f)
+    voice_dir = Path(voice_dir)
+    entry = voices_registry.get(f"{voice_dir.parent.name}/{voice_dir.name}")
+    if not entry:
+        return None
+    info = (entry.get("files") or {}).get(relative_path)
+    return (info or {}).get("sha256_sum") or None
+
+
 class B200Voice:
     """Drop-in for the ids->audio half of ``Mimic3Voice`` backed by libm3b200."""
 
@@ -217,8 +233,13 @@ class B200Voice:
     @staticmethod
     def load_from_directory(voice_dir, session_options=None, providers=None, share_models: bool = True,
                             use_deterministic_compute: bool = False, device: typing.Optional[int] = None,
-                            ) -> "B200Voice":
+                            weight_cache_dir=None, voices_registry=None) -> "B200Voice":
+        """``weight_cache_dir``: directory of packed-weight blobs (one-time conversion of generator.onnx, re-read on
+        later loads; ``None`` = ``$M3B200_WEIGHT_CACHE``).  ``voices_registry``: the reference's ``voices.json``
+        (path or parsed dict, ``mimic3_tts/_resources.py:35-51``): when the voice is listed there, generator.onnx
+        must have the registry's ``sha256_sum`` (the check ``download.py:108-117`` makes) or loading raises."""
         voice_dir = Path(voice_dir)
+        expected_sha256 = registry_sha256(voice_dir, voices_registry) if voices_registry is not None else None
         _LOGGER.debug("Loading voice from %s", voice_dir)
         with open(voice_dir / "config.json", "r", encoding="utf-8") as config_file:
             config = VoiceConfig.load(config_file)
@@ -231,13 +252,14 @@ class B200Voice:
                 onnx_model = B200Voice._SHARED_MODELS.get(model_key)
                 if onnx_model is None:
                     onnx_model = B200Voice._load_model(generator_path, session_options, providers,
-                                                       use_deterministic_compute, device)
+                                                       use_deterministic_compute, device,
+                                                       weight_cache_dir, expected_sha256)
                     B200Voice._SHARED_MODELS[model_key] = onnx_model
                 else:
                     _LOGGER.debug("Using shared B200 model (%s)", model_key)
         else:
             onnx_model = B200Voice._load_model(generator_path, session_options, providers,
-                                               use_deterministic_compute, device)
+                                               use_deterministic_compute, device, weight_cache_dir, expected_sha256)
         phoneme_map = None
         phoneme_map_path = voice_dir / "phoneme_map.txt"
         if phoneme_map_path.is_file():
@@ -261,6 +283,8 @@ class B200Voice:
     # -- voice.py:378-407 ------------------------------------------------------------------------
     @staticmethod
     def _load_model(generator_path, session_options=None, providers=None,
-                    use_deterministic_compute: bool = False, device: typing.Optional[int] = None) -> B200Session:
+                    use_deterministic_compute: bool = False, device: typing.Optional[int] = None,
+                    weight_cache_dir=None, expected_sha256: typing.Optional[str] = None) -> B200Session:
         _LOGGER.debug("Loading model from %s", generator_path)
-        return B200Session(str(generator_path), sess_options=session_options, providers=providers, device=device)
+        return B200Session(str(generator_path), sess_options=session_options, providers=providers, device=device,
+                           cache_dir=weight_cache_dir, expected_sha256=expected_sha256)
