@@ -160,6 +160,51 @@ int64_t m3_result_kernel_launches(const m3_result* r);        /* kernels this ca
 int32_t m3_result_tensor(const m3_result* r, const char* name, const float** data, int64_t* rows, int64_t* cols);
 void m3_result_free(m3_result* r);
 
+/* ---- phonemes -> ids: the step immediately before the engine --------------------------
+ * Replaces phonemes2ids.load_phoneme_ids / load_phoneme_map (mimic3_tts/voice.py:268-271, 302-307) and
+ * phonemes2ids.phonemes2ids as called by Mimic3Voice.phonemes_to_ids (voice.py:126-152) with the voice's
+ * PhonemesConfig (mimic3_tts/config.py:147-176).  Strings are NUL-terminated UTF-8; NULL = Python's None. */
+typedef struct m3_phoneme_table m3_phoneme_table; /* phoneme -> id and phoneme -> [phoneme...] hash tables */
+#define M3_PH_AUTO_BOS_EOS 1u
+#define M3_PH_BLANK_AT_START 2u
+#define M3_PH_BLANK_AT_END 4u
+#define M3_PH_SIMPLE_PUNCTUATION 8u
+#define M3_PH_SEPARATE_GRAPHEMES 16u
+#define M3_PH_SEPARATE_TONES 32u
+#define M3_PH_TONE_BEFORE 64u
+#define M3_PH_BLANK_BETWEEN_TOKENS 0
+#define M3_PH_BLANK_BETWEEN_WORDS 1
+#define M3_PH_BLANK_BETWEEN_TOKENS_AND_WORDS 2
+typedef struct m3_phoneme_opts {          /* PhonemesConfig fields, config.py:147-176 */
+  uint32_t struct_size;
+  uint32_t flags;                         /* M3_PH_*                                                        */
+  int32_t blank_between;                  /* M3_PH_BLANK_BETWEEN_*                                          */
+  int32_t n_punctuation;                  /* entries of punctuation_from/to; < 0: the default ; : -> , ? ! -> . */
+  const char* bos;
+  const char* eos;
+  const char* blank;
+  const char* blank_word;
+  const char* const* punctuation_from;
+  const char* const* punctuation_to;
+  const char* const* separate;            /* symbols split off as phonemes of their own (stress marks ...)  */
+  int32_t n_separate;
+  int32_t reserved;
+} m3_phoneme_opts;
+int32_t m3_phoneme_table_create(m3_phoneme_table** out);
+void m3_phoneme_table_free(m3_phoneme_table* table);
+int32_t m3_phoneme_table_load_ids(m3_phoneme_table* table, const char* phonemes_txt);      /* voice.py:268-271 */
+int32_t m3_phoneme_table_load_map(m3_phoneme_table* table, const char* phoneme_map_txt);   /* voice.py:302-307 */
+int32_t m3_phoneme_table_add(m3_phoneme_table* table, const char* phoneme, int64_t id);
+int32_t m3_phoneme_table_add_map(m3_phoneme_table* table, const char* from, const char* const* to, int32_t n_to);
+int64_t m3_phoneme_table_size(const m3_phoneme_table* table);
+int32_t m3_phoneme_table_lookup(const m3_phoneme_table* table, const char* phoneme, int64_t* id);
+/* `phonemes` holds the phonemes of all words back to back, word w has word_lengths[w] of them.  Unknown phonemes are
+ * dropped (fail_on_missing=False, voice.py:151).  *n_out = ids produced; M3_ERR_INVALID if out_cap is smaller (then
+ * *n_out is the size needed).  opts == NULL: phonemes2ids' keyword defaults (no blank symbol, no bos/eos, default punctuation map unused). */
+int32_t m3_phonemes_to_ids(const m3_phoneme_table* table, const m3_phoneme_opts* opts, const char* const* phonemes,
+                           const int32_t* word_lengths, int32_t n_words, int64_t* out_ids, int64_t out_cap,
+                           int64_t* n_out);
+
 /* Diagnostics: runs test #which of the tcgen05/TMEM building blocks on the current device and
  * stores the max abs error against a host reference (negative = CUDA error code). */
 int32_t m3_selftest(int32_t which, double* result);

@@ -86,6 +86,10 @@ int count_sm100() {
 }
 }  // namespace
 
+namespace m3 {
+void set_last_error(const std::string& m) { g_err = m; }
+}  // namespace m3
+
 extern "C" {
 
 const char* m3_version(void) { return "m3b200 0.1.0 (sm_100a)"; }

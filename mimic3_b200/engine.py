@@ -33,6 +33,9 @@ API_SYMBOLS = [
     "m3_result_device_pcm", "m3_result_device_ms", "m3_result_kernel_launches",
     "m3_result_tensor", "m3_result_free", "m3_selftest",
     "m3_infer_ex", "m3_result_stream", "m3_wav_header",
+    "m3_phoneme_table_create", "m3_phoneme_table_free", "m3_phoneme_table_load_ids", "m3_phoneme_table_load_map",
+    "m3_phoneme_table_add", "m3_phoneme_table_add_map", "m3_phoneme_table_size", "m3_phoneme_table_lookup",
+    "m3_phonemes_to_ids",
     "m3_voice_load_ex", "m3_voice_load_stats", "m3_weight_cache_build", "m3_weight_cache_check", "m3_sha256_file",
 ]
 
@@ -79,6 +82,15 @@ class LoadStats(C.Structure):
                 "parse_ms": self.parse_ms, "pack_ms": self.pack_ms, "cache_read_ms": self.cache_read_ms,
                 "hash_ms": self.hash_ms, "upload_ms": self.upload_ms, "total_ms": self.total_ms,
                 "onnx_sha256": self.onnx_sha256.decode(), "cache_file": self.cache_file.decode()}
+
+
+class _PhonemeOpts(C.Structure):
+    """``m3_phoneme_opts`` (include/m3b200.h)."""
+    _fields_ = [("struct_size", C.c_uint32), ("flags", C.c_uint32), ("blank_between", C.c_int32),
+                ("n_punctuation", C.c_int32), ("bos", C.c_char_p), ("eos", C.c_char_p), ("blank", C.c_char_p),
+                ("blank_word", C.c_char_p), ("punctuation_from", C.POINTER(C.c_char_p)),
+                ("punctuation_to", C.POINTER(C.c_char_p)), ("separate", C.POINTER(C.c_char_p)),
+                ("n_separate", C.c_int32), ("reserved", C.c_int32)]
 
 
 LOAD_VERIFY_SHA256 = 1

@@ -174,3 +174,142 @@ def phonemes2ids(word_phonemes: WORD_PHONEMES_TYPE, phoneme_to_id: typing.Mappin
     if blank_at_end and blank_id is not None:
         out.append(blank_id)
     return out
+
+
+class NativePhonemeTable:
+    """phonemes -> ids through ``libm3b200.so`` (``m3_phoneme_table_*`` / ``m3_phonemes_to_ids``, csrc/phonemes.cc):
+    ``phonemes.txt`` and ``phoneme_map.txt`` are read natively into hash tables (``voice.py:268-271, 302-307``) and
+    :meth:`phonemes2ids` takes the keyword arguments of ``phonemes2ids.phonemes2ids`` as
+    ``Mimic3Voice.phonemes_to_ids`` passes them (``voice.py:133-152``).  The table belongs to the object: the
+    ``phoneme_to_id`` / ``phoneme_map`` keywords of a call are accepted for signature compatibility and must be the
+    mappings the table was made from (``None`` / the voice's own)."""
+
+    def __init__(self):
+        import ctypes as C
+        from . import engine
+        self._C = C
+        self._engine = engine
+        self._lib = engine.load_library()
+        lib = self._lib
+        if not getattr(lib, "_m3_ph_bound", False):
+            vp, i32 = C.c_void_p, C.c_int32
+            lib.m3_phoneme_table_create.restype = i32
+            lib.m3_phoneme_table_create.argtypes = [C.POINTER(vp)]
+            lib.m3_phoneme_table_free.restype = None
+            lib.m3_phoneme_table_free.argtypes = [vp]
+            for name in ("m3_phoneme_table_load_ids", "m3_phoneme_table_load_map"):
+                getattr(lib, name).restype = i32
+                getattr(lib, name).argtypes = [vp, C.c_char_p]
+            lib.m3_phoneme_table_add.restype = i32
+            lib.m3_phoneme_table_add.argtypes = [vp, C.c_char_p, C.c_int64]
+            lib.m3_phoneme_table_add_map.restype = i32
+            lib.m3_phoneme_table_add_map.argtypes = [vp, C.c_char_p, C.POINTER(C.c_char_p), i32]
+            lib.m3_phoneme_table_size.restype = C.c_int64
+            lib.m3_phoneme_table_size.argtypes = [vp]
+            lib.m3_phoneme_table_lookup.restype = i32
+            lib.m3_phoneme_table_lookup.argtypes = [vp, C.c_char_p, C.POINTER(C.c_int64)]
+            lib.m3_phonemes_to_ids.restype = i32
+            lib.m3_phonemes_to_ids.argtypes = [vp, C.c_void_p, C.POINTER(C.c_char_p), C.POINTER(i32), i32,
+                                               C.POINTER(C.c_int64), C.c_int64, C.POINTER(C.c_int64)]
+            lib._m3_ph_bound = True
+        h = C.c_void_p()
+        self._check(lib.m3_phoneme_table_create(C.byref(h)))
+        self._h = h
+        self._has_map = False
+
+    def _check(self, rc):
+        if rc != 0:
+            self._engine._raise(self._lib, rc)
+
+    @classmethod
+    def from_files(cls, phonemes_txt, phoneme_map_txt=None) -> "NativePhonemeTable":
+        t = cls()
+        t._check(t._lib.m3_phoneme_table_load_ids(t._h, str(phonemes_txt).encode()))
+        if phoneme_map_txt is not None:
+            t._check(t._lib.m3_phoneme_table_load_map(t._h, str(phoneme_map_txt).encode()))
+            t._has_map = True
+        return t
+
+    @classmethod
+    def from_mappings(cls, phoneme_to_id, phoneme_map=None) -> "NativePhonemeTable":
+        t = cls()
+        for k, v in phoneme_to_id.items():
+            t._check(t._lib.m3_phoneme_table_add(t._h, k.encode("utf-8"), int(v)))
+        t.set_phoneme_map(phoneme_map)
+        return t
+
+    def set_phoneme_map(self, phoneme_map) -> None:
+        """``phoneme_map = self.phoneme_map or self.config.phonemes.phoneme_map`` (voice.py:130): entries are added."""
+        C = self._C
+        for k, v in (phoneme_map or {}).items():
+            to = [v] if isinstance(v, str) else list(v)
+            arr = (C.c_char_p * max(1, len(to)))(*[s.encode("utf-8") for s in to])
+            self._check(self._lib.m3_phoneme_table_add_map(self._h, k.encode("utf-8"), arr, len(to)))
+            self._has_map = True
+
+    def __len__(self) -> int:
+        return int(self._lib.m3_phoneme_table_size(self._h))
+
+    def __getitem__(self, phoneme: str) -> int:
+        out = self._C.c_int64()
+        rc = self._lib.m3_phoneme_table_lookup(self._h, phoneme.encode("utf-8"), self._C.byref(out))
+        if rc != 0:
+            raise KeyError(phoneme)
+        return int(out.value)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.m3_phoneme_table_free(self._h)
+            self._h = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def phonemes2ids(self, word_phonemes, phoneme_to_id=None, pad=None, bos=None, eos=None, auto_bos_eos=False,
+                     blank=None, blank_word=None, blank_between=BlankBetween.WORDS, blank_at_start=True,
+                     blank_at_end=True, simple_punctuation=False, punctuation_map=None, separate=None,
+                     separate_graphemes=False, separate_tones=False, tone_before=False, phoneme_map=None,
+                     fail_on_missing=False, missing_func=None) -> typing.List[int]:
+        C = self._C
+        if fail_on_missing or missing_func is not None:
+            raise NotImplementedError("the native table drops unknown phonemes (voice.py:151 passes fail_on_missing=False)")
+        from .engine import _PhonemeOpts
+        enc = lambda s: None if s is None else s.encode("utf-8")
+        o = _PhonemeOpts()
+        o.struct_size = C.sizeof(_PhonemeOpts)
+        o.flags = ((1 if auto_bos_eos else 0) | (2 if blank_at_start else 0) | (4 if blank_at_end else 0)
+                   | (8 if simple_punctuation else 0) | (16 if separate_graphemes else 0)
+                   | (32 if separate_tones else 0) | (64 if tone_before else 0))
+        o.blank_between = {"tokens": 0, "words": 1, "tokens_and_words": 2}[BlankBetween(blank_between).value]
+        o.bos, o.eos, o.blank, o.blank_word = enc(bos), enc(eos), enc(blank), enc(blank_word)
+        keep = []
+        if punctuation_map is None:
+            o.n_punctuation = -1
+        else:
+            items = list(punctuation_map.items())
+            pf = (C.c_char_p * max(1, len(items)))(*[k.encode("utf-8") for k, _ in items])
+            pt = (C.c_char_p * max(1, len(items)))(*[v.encode("utf-8") for _, v in items])
+            keep += [pf, pt]
+            o.punctuation_from, o.punctuation_to, o.n_punctuation = pf, pt, len(items)
+        seps = sorted(set(separate or ()), key=len, reverse=True)
+        if seps:
+            sa = (C.c_char_p * len(seps))(*[s.encode("utf-8") for s in seps])
+            keep.append(sa)
+            o.separate, o.n_separate = sa, len(seps)
+        flat = [p.encode("utf-8") for w in word_phonemes for p in w]
+        lens = [len(w) for w in word_phonemes]
+        ph = (C.c_char_p * max(1, len(flat)))(*flat)
+        wl = (C.c_int32 * max(1, len(lens)))(*lens)
+        cap = 4 * len(flat) + 2 * len(lens) + 16
+        n = C.c_int64()
+        while True:
+            out = (C.c_int64 * cap)()
+            rc = self._lib.m3_phonemes_to_ids(self._h, C.byref(o), ph, wl, len(lens), out, cap, C.byref(n))
+            if rc != 0 and n.value > cap:   # splitting / mapping produced more ids than estimated
+                cap = int(n.value)
+                continue
+            self._check(rc)
+            return list(out[: n.value])

@@ -36,10 +36,13 @@ try:
         raise ImportError  # a test registered the restatement under that name
     PHONEMES2IDS_SOURCE = "phonemes2ids"
 except ImportError:
+    # without the package: load_from_directory builds a native table (csrc/phonemes.cc through libm3b200.so, see
+    # NativePhonemeTable); the Python restatement below is what a bare B200Voice(...) falls back to and what the
+    # native code is fuzzed against
     from .phonemes import load_phoneme_ids, load_phoneme_map, phonemes2ids
     PHONEMES2IDS_SOURCE = "mimic3_b200.phonemes"
-    _LOGGER.warning("phonemes2ids is not installed: using the in-repo restatement (mimic3_b200.phonemes; parity with "
-                    "the package is pinned by its documented behaviour only)")
+    _LOGGER.info("phonemes2ids is not installed: phonemes -> ids runs natively in libm3b200 (parity with the package is "
+                 "pinned by its documented behaviour only)")
 
 DEFAULT_RATE = 1.0
 DEFAULT_VOLUME = 100.0   # mimic3_tts/const.py
@@ -277,8 +280,17 @@ class B200Voice:
                     speaker_id = int(row[0])
                     for alias in row[2:]:
                         speaker_map[alias] = speaker_id
+        fn = None
+        if PHONEMES2IDS_SOURCE != "phonemes2ids":
+            # native table lookup: phonemes.txt / phoneme_map.txt read by the C library
+            from .phonemes import NativePhonemeTable
+            table = NativePhonemeTable.from_files(voice_dir / "phonemes.txt",
+                                                  phoneme_map_path if phoneme_map_path.is_file() else None)
+            if phoneme_map is None:
+                table.set_phoneme_map(getattr(config.phonemes, "phoneme_map", None))
+            fn = table.phonemes2ids
         return B200Voice(config=config, onnx_model=onnx_model, phoneme_to_id=phoneme_to_id,
-                         phoneme_map=phoneme_map, speaker_map=speaker_map)
+                         phoneme_map=phoneme_map, speaker_map=speaker_map, phonemes_to_ids_fn=fn)
 
     # -- voice.py:378-407 ------------------------------------------------------------------------
     @staticmethod
