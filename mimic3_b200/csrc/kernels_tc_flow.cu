@@ -277,9 +277,7 @@ __global__ void __launch_bounds__(FL_THREADS, 1) flow_tc_kernel(FlowTcParams p) 
         for (int e = 0; e < 8; ++e) {
           const float a0 = va[2 * e] + ba[2 * e], a1 = va[2 * e + 1] + ba[2 * e + 1];
           const float g0 = vb[2 * e] + bb[2 * e], g1 = vb[2 * e + 1] + bb[2 * e + 1];
-          const float o0v = tanhf(a0) * (1.f / (1.f + expf(-g0)));
-          const float o1v = tanhf(a1) * (1.f / (1.f + expf(-g1)));
-          pk[e] = E::pack2(o0v, o1v);
+          pk[e] = E::pack2(tc::gate_tanh_sigmoid(a0, g0), tc::gate_tanh_sigmoid(a1, g1));
         }
         uint8_t* d = bufA + (size_t(ch0 / 8) * ROWS_A + r) * 16;
         *reinterpret_cast<uint4*>(d) = make_uint4(pk[0], pk[1], pk[2], pk[3]);

@@ -185,6 +185,19 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// WaveNet gate tanh(a) * sigmoid(g) on the SFU: with t = 2^(-2|a| log2 e) and u = 2^(-g log2 e),
+//     tanh(a) * sigmoid(g) = sign(a) * (1 - t) / ((1 + t) * (1 + u))
+// -- two ex2.approx + one rcp.approx (a few ulp each) instead of tanhf + expf + an IEEE division (~60 instructions per
+// element; the ncu source page of flow_tc_kernel put 35 % of the epilogue warps' samples on those two lines).
+// t <= 1 always; u = +inf (g << 0) gives rcp(inf) = 0, the correct limit.
+__device__ __forceinline__ float gate_tanh_sigmoid(float a, float g) {
+  float t, u, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(-2.885390081777927f * fabsf(a)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(u) : "f"(-1.4426950408889634f * g));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"((1.f + t) * (1.f + u)));
+  return copysignf((1.f - t) * r, a);
+}
+
 // ---- operand element types ------------------------------------------------------------------------
 template <int FMT>
 struct Elem;
