@@ -493,6 +493,54 @@ PackedVoice pack_voice(const HostVoice& hv) {
         B.place(&cw.ftc.skip_bias, skb);
         B.place(&cw.ftc.post_bias, pob);
         cw.ftc.ok = true;
+
+        // ---- second-generation stream (kernels_tc_flow2.cu): every block [K/8][N][8] with K x N = 192 x 96 or 96 x 192
+        if (flow2_tc_supported(Hf, half, nl, dv.flow_kernel)) {
+          while (B.h16.size() % 64) B.h16.push_back(0);
+          cw.ftc.woff2 = B.h16.size();
+          auto block = [&](int K, int N, auto&& wfun) {  // wfun(k, n) -> weight of input k, output column n
+            const size_t o = B.h16.size();
+            B.h16.resize(o + size_t(K) * N, 0);
+            for (int k = 0; k < K; ++k)
+              for (int n = 0; n < N; ++n) B.h16[o + (size_t(k / 8) * N + n) * 8 + (k & 7)] = B.cvt16(float(wfun(k, n)));
+          };
+          block(half, Hf, [&](int k, int n) { return wpre.f32[size_t(n) * half + perm(k)]; });
+          std::vector<double> mb(half, 0.0);
+          for (int n = 0; n < half; ++n) {
+            double acc = bpo.f32[perm(n)];
+            for (int sidx = 0; sidx < Hf; ++sidx) acc += double(wpo.f32[size_t(perm(n)) * Hf + sidx]) * double(skb[sidx]);
+            mb[n] = acc;
+          }
+          for (int i = 0; i < nl; ++i) {
+            const std::string is = std::to_string(i);
+            const OnnxTensor& win = hv.need(p + ".enc.in_layers." + is + ".weight", {2 * Hf, Hf, dv.flow_kernel});
+            const int rsn = i < nl - 1 ? 2 * Hf : Hf;
+            const OnnxTensor& wrs = hv.need(p + ".enc.res_skip_layers." + is + ".weight", {rsn, Hf, 1});
+            for (int cc = 0; cc < Hf / 48; ++cc)
+              for (int tap = 0; tap < dv.flow_kernel; ++tap)
+                block(Hf, 96, [&](int k, int j) {
+                  const int ch = (j < 48 ? 0 : Hf) + 48 * cc + (j % 48);
+                  return win.f32[(size_t(ch) * Hf + k) * dv.flow_kernel + tap];
+                });
+            if (i < nl - 1)
+              for (int kh = 0; kh < 2; ++kh)
+                block(Hf / 2, Hf, [&](int k, int n) { return wrs.f32[size_t(n) * Hf + kh * (Hf / 2) + k]; });
+            // m-update: W'[n][k] = sum_s W_post[perm(n)][s] . W_skip_i[s][k]  (fp64 on the host, one rounding to 16 bits)
+            const size_t skip_row0 = i < nl - 1 ? size_t(Hf) : 0;
+            std::vector<double> wp(size_t(half) * Hf, 0.0);
+            for (int n = 0; n < half; ++n)
+              for (int sidx = 0; sidx < Hf; ++sidx) {
+                const double a = wpo.f32[size_t(perm(n)) * Hf + sidx];
+                const float* wrow = &wrs.f32[(skip_row0 + sidx) * Hf];
+                double* dst = &wp[size_t(n) * Hf];
+                for (int k = 0; k < Hf; ++k) dst[k] += a * double(wrow[k]);
+              }
+            block(Hf, half, [&](int k, int n) { return wp[size_t(n) * Hf + k]; });
+          }
+          std::vector<float> mbf(mb.begin(), mb.end());
+          B.place(&cw.ftc.m_bias, mbf);
+          cw.ftc.ok2 = B.h16.size() - cw.ftc.woff2 == flow2_tc_weight_elems(nl);
+        }
       }
     }
   }
@@ -1297,7 +1345,13 @@ Result* run_inference(Voice& v, const int64_t* ids, const int64_t* lengths, int 
       }
       fp.seg_off = d_frm_off;
       fp.seg_len = d_frm_len;
-      launch_flow_tc(fp, dv.tc_fmt, batch, Fmax, st);
+      if (cw.ftc.ok2 && !getenv("M3B200_FLOW_V1")) {  // second-generation kernel: fewer, wider MMAs (kernels_tc_flow2.cu)
+        fp.w = dv.slab16 + cw.ftc.woff2;
+        fp.post_bias = cw.ftc.m_bias;
+        launch_flow2_tc(fp, dv.tc_fmt, batch, Fmax, st);
+      } else {
+        launch_flow_tc(fp, dv.tc_fmt, batch, Fmax, st);
+      }
     }
     for (size_t f = 0; !fused && f < dv.couplings.size(); ++f) {
       const CouplingW& cw = dv.couplings[f];

@@ -69,6 +69,10 @@ struct FlowTcW {  // fused coupling-layer packing (kernels_tc_flow.cu)
   unsigned long long woff = 0;
   const float *in_bias = nullptr, *cum_bias = nullptr, *skip_bias = nullptr, *post_bias = nullptr;
   int x0_coff = 0, x1_coff = 0;
+  // second-generation kernel (kernels_tc_flow2.cu): 36 864-byte blocks in its schedule order, post folded into the skips
+  bool ok2 = false;
+  unsigned long long woff2 = 0;
+  const float* m_bias = nullptr;  // [half]: post bias + W_post . (sum of the skip biases), flip-permuted
 };
 
 struct CouplingW {

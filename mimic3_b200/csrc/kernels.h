@@ -202,6 +202,7 @@ struct DecFusedParams {
   const int* seg_len = nullptr;
   int H = 0, HX = 0, HYb[3] = {};  // HYb: halo rows of resblock j's second-conv operand buffer (>= 3 for j = 0: conv_post reuses it)
   int stride = 0, n_seg = 0, max_win = 0;  // filled by the launcher
+  long long* prof = nullptr;               // M3B200_DEC_PROFILE=1: per-role cycle counters (debug)
 };
 bool dec_fused_supported(int C, int cin, int up_k, int up_u, int nk, int nd, int HX, const int* HYb, size_t w_bytes);
 void launch_dec_fused(const DecFusedParams& p, int fmt, int n_seg, int max_len, cudaStream_t st);
@@ -220,11 +221,18 @@ struct FlowTcParams {
   const float* post_bias = nullptr;  // [half] (flip-permuted)
   const float* cond = nullptr;       // per utterance [cond_stride], laid out like in_bias; may be null
   int cond_stride = 0;
+  long long* prof = nullptr;         // M3B200_FLOW_PROFILE=1: per-role cycle counters (debug)
   const int* seg_off = nullptr;
   const int* seg_len = nullptr;
 };
 bool flow_tc_supported(int Hc, int half, int nl, int kernel);
 void launch_flow_tc(const FlowTcParams& p, int fmt, int n_seg, int max_len, cudaStream_t st);
+// Second generation (kernels_tc_flow2.cu): same params; `w` is the v2 stream (pre K96xN192 | per layer: 4 gate chunks x 5
+// taps K192xN96 (48 "a" + 48 "b" columns), [res K-halves 2 x K96xN192], m-update K192xN96 with W' = W_post.W_skip),
+// `post_bias` = m_bias; skip_bias unused.
+bool flow2_tc_supported(int Hc, int half, int nl, int kernel);
+size_t flow2_tc_weight_elems(int nl);
+void launch_flow2_tc(const FlowTcParams& p, int fmt, int n_seg, int max_len, cudaStream_t st);
 
 bool mrf_tc_supported(int C, int nk, int nd, const int* k, int max_halo);
 // persistent warp-specialised variant for C = 64, three ResBlock2 chains (kernels_tc_mrf2.cu)

@@ -18,6 +18,7 @@
 //     accumulate into one TMEM tile S.
 // TMEM (512 columns): T_j = [96 j, 96 j + 96) conv1 accumulators, S = [288, 384) (conv_post reuses it),
 // D = [384, 512) transposed-conv result.
+#include <cstdio>
 #include <cstdlib>
 #include <stdexcept>
 #include <type_traits>
@@ -29,7 +30,7 @@ namespace m3 {
 
 namespace {
 constexpr int kC = 32, kNT = 3, kR = kNT * 128, kCH = kC / 8;
-constexpr int kEpiWarps = 8, kIssuer = 8, kLoader = 9, kLoaders = 3, kThreads = 32 * (kLoader + kLoaders);
+constexpr int kLoaders = 3;  // warp roles: NEW epilogue warps (8 or 16), one issuer, kLoaders loader warps
 constexpr int kLoadDepth = 9;   // y_prev rows-chunks in flight per loader lane (one round for u = 4)
 constexpr uint32_t kT0 = 0, kS0 = 288, kD0 = 384;
 constexpr int kSegTable = 1024;
@@ -60,13 +61,21 @@ __host__ __device__ inline Geo make_geo(const DecFusedParams& p) {
   return g;
 }
 
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;\n" ::: "memory"); }
+template <int NTHR>
+__device__ __forceinline__ void epi_bar_n() { asm volatile("bar.sync 1, %0;\n" ::"n"(NTHR) : "memory"); }
 __device__ __forceinline__ float lrelu(float v, float s) { return fmaxf(v, s * v); }
 }  // namespace
 
-template <int FMT>
-__global__ void __launch_bounds__(kThreads, 1) dec_fused_kernel(DecFusedParams p) {
+// NEW = epilogue warps: 8 (16 of the 32 channels per thread) or 16 (8 channels per thread: half the dependent
+// tmem_ld -> math -> st.shared chain per thread and twice the warps to hide its latency; the M3B200_DEC_PROFILE counters
+// show the epilogue warps are busy 86 % of a window while the issuer waits for them 28 % of it)
+template <int FMT, int NEW>
+__global__ void __maxnreg__(NEW == 16 ? 96 : 168) dec_fused_kernel(DecFusedParams p) {
   using E = tc::Elem<FMT>;
+  constexpr int kEpiWarps = NEW, kIssuer = NEW, kLoader = NEW + 1, kThreads = 32 * (kLoader + kLoaders);
+  constexpr int NCG = NEW / 4, G = kC / NCG;  // column groups and channels per thread (16 or 8)
+  constexpr int kLD = NEW == 16 ? 5 : kLoadDepth;  // loads in flight per loader lane (96 registers per thread with 16 epilogue warps)
+  auto epi_bar = [] { epi_bar_n<32 * NEW>(); };
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(8) uint64_t bars[NBAR];
@@ -124,6 +133,20 @@ __global__ void __launch_bounds__(kThreads, 1) dec_fused_kernel(DecFusedParams p
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem = tmem_slot;
+#ifdef M3B200_KERNEL_PROFILE  // per-role cycle counters (M3B200_DEC_PROFILE=1); compiled out by default: +9 % kernel time when merely present
+  const bool prof = p.prof != nullptr;
+#else
+  constexpr bool prof = false;
+#endif
+  auto timed_wait = [&](uint64_t* bar, uint32_t parity, long long& acc) {
+    if (prof && !tc::mbar_test(bar, parity)) {  // only waits that actually block are timed
+      const long long t = clock64();
+      tc::mbar_wait(bar, parity);
+      acc += clock64() - t;
+    } else {
+      tc::mbar_wait(bar, parity);
+    }
+  };
 
   if (warp >= kLoader) {
     // =================================== loader warp ===============================================
@@ -149,11 +172,11 @@ __global__ void __launch_bounds__(kThreads, 1) dec_fused_kernel(DecFusedParams p
         const int e = w0 + p.up_pad;
         const int tq0 = e >= 0 ? e / u : -((-e + u - 1) / u);
         const int lt = (warp - kLoader) * 32 + lane;
-        for (int i0 = lt; i0 < items; i0 += 32 * kLoaders * kLoadDepth) {  // all global loads of a round in flight together
-          float4 a[kLoadDepth], b[kLoadDepth];
-          bool ok[kLoadDepth];
+        for (int i0 = lt; i0 < items; i0 += 32 * kLoaders * kLD) {  // all global loads of a round in flight together
+          float4 a[kLD], b[kLD];
+          bool ok[kLD];
 #pragma unroll
-          for (int k = 0; k < kLoadDepth; ++k) {
+          for (int k = 0; k < kLD; ++k) {
             const int i = i0 + 32 * kLoaders * k;
             const int ra = i / CHI, c8 = i - ra * CHI;
             const int t = tq0 - 1 + ra;
@@ -165,7 +188,7 @@ __global__ void __launch_bounds__(kThreads, 1) dec_fused_kernel(DecFusedParams p
             }
           }
 #pragma unroll
-          for (int k = 0; k < kLoadDepth; ++k) {
+          for (int k = 0; k < kLD; ++k) {
             const int i = i0 + 32 * kLoaders * k;
             if (i >= items) continue;
             const int ra = i / CHI, c8 = i - ra * CHI;
@@ -239,8 +262,10 @@ __global__ void __launch_bounds__(kThreads, 1) dec_fused_kernel(DecFusedParams p
       const uint32_t aX = tc::smem_u32(bufX);
       // ONE elected thread runs the whole schedule, waits included: no warp reconvergence between convs
       if (tc::elect_one()) {
+        long long c_x = 0, c_y = 0, c_a = 0, c_o = 0;
         tc::mbar_wait(&bars[W_FULL], 0u);
         tc::mbar_wait(&bars[A_FULL], 0u);
+        const long long c_start = prof ? clock64() : 0;
         tc::fence_after_sync();
         issue_up();
         tc::mma_commit(&bars[U_DONE]);
@@ -248,44 +273,53 @@ __global__ void __launch_bounds__(kThreads, 1) dec_fused_kernel(DecFusedParams p
         for (int idx = first; idx < total; ++it) {
           const int nxt = next_item(idx);
           const uint32_t par = uint32_t(it) & 1u;
-          tc::mbar_wait(&bars[X_READY], par);
+          timed_wait(&bars[X_READY], par, c_x);
           tc::fence_after_sync();
           for (int j = 0; j < 3; ++j) {
             issue(I2{}, I3{}, aX, g.rows_x, p.HX, p.c1[j], kC, kT0 + uint32_t(j) * 96u, kC, idC, false);
             tc::mma_commit(&bars[C1_DONE + j]);
           }
           for (int j = 0; j < 3; ++j) {
-            tc::mbar_wait(&bars[Y_READY + j], par);
+            timed_wait(&bars[Y_READY + j], par, c_y);
             tc::fence_after_sync();
             issue(I2{}, I3{}, tc::smem_u32(smem + g.off_y[j]), g.rows_y[j], p.HYb[j], p.c2[j], kC, kS0, kC, idC, j > 0);
           }
           tc::mma_commit(&bars[C2_DONE]);
           if (nxt < total) {  // next window's transposed conv fills the gap while the epilogue reduces this one
-            tc::mbar_wait(&bars[A_FULL], uint32_t(it + 1) & 1u);
+            timed_wait(&bars[A_FULL], uint32_t(it + 1) & 1u, c_a);
             tc::fence_after_sync();
             issue_up();
             tc::mma_commit(&bars[U_DONE]);
           }
-          tc::mbar_wait(&bars[O_READY], par);
+          timed_wait(&bars[O_READY], par, c_o);
           tc::fence_after_sync();
           issue(I2{}, I3{}, tc::smem_u32(smem + g.off_y[0]), g.rows_y[0], p.HYb[0], p.post, 16, kS0, 16, idP, false);
           tc::mma_commit(&bars[P_DONE]);
           idx = nxt;
+        }
+        if (prof) {
+          unsigned long long* q = reinterpret_cast<unsigned long long*>(p.prof);
+          atomicAdd(q + 0, (unsigned long long)(clock64() - c_start));
+          atomicAdd(q + 1, (unsigned long long)c_x);
+          atomicAdd(q + 2, (unsigned long long)c_y);
+          atomicAdd(q + 3, (unsigned long long)c_a);
+          atomicAdd(q + 4, (unsigned long long)c_o);
+          atomicAdd(q + 5, (unsigned long long)it);
         }
       }
       __syncwarp();
     }
   } else {
     // =================================== epilogue warps ============================================
-    const int q = warp & 3, hhalf = warp >> 2;
+    const int q = warp & 3, hhalf = warp >> 2;  // hhalf: column group 0..NCG-1
     const uint32_t lane_base = tmem + (uint32_t(q * 32) << 16);
-    const int col0 = hhalf * 16;
-    float xr[kNT][16], xs[kNT][16];
+    const int col0 = hhalf * G;
+    float xr[kNT][G], xs[kNT][G];
 
-    auto store_y = [&](uint8_t* buf, int pitch, int row, const uint32_t* pk) {  // 16 columns = 2 chunks of 8
+    auto store_y = [&](uint8_t* buf, int pitch, int row, const uint32_t* pk) {  // G columns = G / 8 chunks of 8
       uint8_t* dst = buf + (size_t(col0 / 8) * pitch + row) * 16;
       *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-      *reinterpret_cast<uint4*>(dst + size_t(pitch) * 16) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      if constexpr (G == 16) *reinterpret_cast<uint4*>(dst + size_t(pitch) * 16) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
     };
     auto arrive = [&](int b) {
       tc::fence_async_smem();
@@ -293,8 +327,10 @@ __global__ void __launch_bounds__(kThreads, 1) dec_fused_kernel(DecFusedParams p
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&bars[b]);
     };
+    long long e_u = 0, e_p = 0, e_c1 = 0, e_c2 = 0;
+    const long long e_start = prof ? clock64() : 0;
     auto post_epi = [&](int seg, int w0, int L, long long base, uint32_t par) {
-      tc::mbar_wait(&bars[P_DONE], par);
+      timed_wait(&bars[P_DONE], par, e_p);
       tc::fence_after_sync();
       if (hhalf == 0) {
         float mx = 0.f;
@@ -334,12 +370,12 @@ __global__ void __launch_bounds__(kThreads, 1) dec_fused_kernel(DecFusedParams p
       // ---- transposed-conv epilogue: D[t][ph*C + co] -> x in sample order ----
       // pass 1 (lane = y_prev row): x = D + b into the fp32 staging tile, 16-byte chunks XOR-swizzled so that
       // both this strided write (rows u apart) and the row-per-lane read below are bank-conflict free
-      tc::mbar_wait(&bars[U_DONE], par);
+      timed_wait(&bars[U_DONE], par, e_u);
       tc::fence_after_sync();
       for (int mt = 0; mt < g.nmu; ++mt) {
         const int lq = mt * 128 + q * 32 + lane;
-        for (int pp = 0; pp < u / 2; ++pp) {
-          const int ph = hhalf * (u / 2) + pp;
+        for (int pp = 0; pp < u / NCG; ++pp) {
+          const int ph = hhalf * (u / NCG) + pp;
           float v[32];
           tc::tmem_ld16(lane_base + kD0 + uint32_t(mt * NUP + ph * kC), v);
           tc::tmem_ld16(lane_base + kD0 + uint32_t(mt * NUP + ph * kC + 16), v + 16);
@@ -373,16 +409,16 @@ __global__ void __launch_bounds__(kThreads, 1) dec_fused_kernel(DecFusedParams p
         const int key = (r & 7) ^ ((r >> 3) & 3);
         const uint8_t* xrow = XS + size_t(r) * 128;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const float4 f = *reinterpret_cast<const float4*>(xrow + (((hhalf * 4 + c) ^ key) << 4));
+        for (int c = 0; c < G / 4; ++c) {
+          const float4 f = *reinterpret_cast<const float4*>(xrow + (((hhalf * (G / 4) + c) ^ key) << 4));
           xr[m][4 * c] = f.x;
           xr[m][4 * c + 1] = f.y;
           xr[m][4 * c + 2] = f.z;
           xr[m][4 * c + 3] = f.w;
         }
-        uint32_t pk[8];
+        uint32_t pk[G / 2];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) pk[c] = inside ? E::pack2(lrelu(xr[m][2 * c], 0.1f), lrelu(xr[m][2 * c + 1], 0.1f)) : 0u;
+        for (int c = 0; c < G / 2; ++c) pk[c] = inside ? E::pack2(lrelu(xr[m][2 * c], 0.1f), lrelu(xr[m][2 * c + 1], 0.1f)) : 0u;
         store_y(bufX, g.rows_x, r + p.HX, pk);
       }
       arrive(X_READY);
@@ -403,13 +439,13 @@ __global__ void __launch_bounds__(kThreads, 1) dec_fused_kernel(DecFusedParams p
       // ---- first conv of each resblock: x1 = x + b + conv(lrelu x); operand of the second conv = lrelu(x1) ----
 #pragma unroll 1
       for (int j = 0; j < 3; ++j) {
-        tc::mbar_wait(&bars[C1_DONE + j], par);
+        timed_wait(&bars[C1_DONE + j], par, e_c1);
         tc::fence_after_sync();
         uint8_t* by = smem + g.off_y[j];
         const int pitch = g.rows_y[j], hy = p.HYb[j];
-        float bj[16];
+        float bj[G];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < G / 4; ++c) {
           const float4 f = *reinterpret_cast<const float4*>(&sbias[1 + j][col0 + 4 * c]);
           bj[4 * c] = f.x;
           bj[4 * c + 1] = f.y;
@@ -418,34 +454,34 @@ __global__ void __launch_bounds__(kThreads, 1) dec_fused_kernel(DecFusedParams p
         }
 #pragma unroll
         for (int m = 0; m < kNT; ++m) {
-          float v[16];
-          tc::tmem_ld16(lane_base + kT0 + uint32_t(j * 96 + m * kC + col0), v);
+          float v[G];
+          tc::tmem_ldg<G>(lane_base + kT0 + uint32_t(j * 96 + m * kC + col0), v);
           tc::tmem_ld_wait();
           const int r = m * 128 + q * 32 + lane;
           const int gi = w0 + r;
           const bool inside = gi >= 0 && gi < L;
-          uint32_t pk[8];
+          uint32_t pk[G / 2];
 #pragma unroll
-          for (int c = 0; c < 16; ++c) {
+          for (int c = 0; c < G; ++c) {
             v[c] += xr[m][c] + bj[c];
             xs[m][c] = j == 0 ? v[c] : xs[m][c] + v[c];
           }
 #pragma unroll
-          for (int c = 0; c < 8; ++c) pk[c] = inside ? E::pack2(lrelu(v[2 * c], 0.1f), lrelu(v[2 * c + 1], 0.1f)) : 0u;
+          for (int c = 0; c < G / 2; ++c) pk[c] = inside ? E::pack2(lrelu(v[2 * c], 0.1f), lrelu(v[2 * c + 1], 0.1f)) : 0u;
           store_y(by, pitch, r + hy, pk);
         }
         arrive(Y_READY + j);
       }
 
       // ---- out = (sum_j x1_j + S + late bias) / nk; operand of conv_post = lrelu(out, 0.01) in bufY0 ----
-      tc::mbar_wait(&bars[C2_DONE], par);
+      timed_wait(&bars[C2_DONE], par, e_c2);
       tc::fence_after_sync();
       {
         uint8_t* by = smem + g.off_y[0];
         const int pitch = g.rows_y[0], hy = p.HYb[0];
-        float bl[16];
+        float bl[G];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < G / 4; ++c) {
           const float4 f = *reinterpret_cast<const float4*>(&sbias[4][col0 + 4 * c]);
           bl[4 * c] = f.x;
           bl[4 * c + 1] = f.y;
@@ -454,17 +490,17 @@ __global__ void __launch_bounds__(kThreads, 1) dec_fused_kernel(DecFusedParams p
         }
 #pragma unroll
         for (int m = 0; m < kNT; ++m) {
-          float v[16];
-          tc::tmem_ld16(lane_base + kS0 + uint32_t(m * kC + col0), v);
+          float v[G];
+          tc::tmem_ldg<G>(lane_base + kS0 + uint32_t(m * kC + col0), v);
           tc::tmem_ld_wait();
           const int r = m * 128 + q * 32 + lane;
           const int gi = w0 + r;
           const bool inside = gi >= 0 && gi < L;
-          uint32_t pk[8];
+          uint32_t pk[G / 2];
 #pragma unroll
-          for (int c = 0; c < 16; ++c) v[c] = lrelu((v[c] + xs[m][c] + bl[c]) * p.inv_nk, 0.01f);
+          for (int c = 0; c < G; ++c) v[c] = lrelu((v[c] + xs[m][c] + bl[c]) * p.inv_nk, 0.01f);
 #pragma unroll
-          for (int c = 0; c < 8; ++c) pk[c] = inside ? E::pack2(v[2 * c], v[2 * c + 1]) : 0u;
+          for (int c = 0; c < G / 2; ++c) pk[c] = inside ? E::pack2(v[2 * c], v[2 * c + 1]) : 0u;
           store_y(by, pitch, r + hy, pk);
         }
       }
@@ -475,6 +511,14 @@ __global__ void __launch_bounds__(kThreads, 1) dec_fused_kernel(DecFusedParams p
       pbase = base;
     }
     if (it > 0) post_epi(pseg, pw0, pL, pbase, uint32_t(it - 1) & 1u);
+    if (prof && tid == 0) {
+      unsigned long long* q = reinterpret_cast<unsigned long long*>(p.prof);
+      atomicAdd(q + 8, (unsigned long long)(clock64() - e_start));
+      atomicAdd(q + 9, (unsigned long long)e_u);
+      atomicAdd(q + 10, (unsigned long long)e_p);
+      atomicAdd(q + 11, (unsigned long long)e_c1);
+      atomicAdd(q + 12, (unsigned long long)e_c2);
+    }
   }
   tc::fence_before_sync();
   __syncthreads();
@@ -517,13 +561,39 @@ void launch_dec_fused(const DecFusedParams& p_in, int fmt, int n_seg, int max_le
     return n;
   }();
   const size_t smem = dec_fused_smem_bytes(p);
-  const void* kern = fmt ? reinterpret_cast<const void*>(dec_fused_kernel<1>) : reinterpret_cast<const void*>(dec_fused_kernel<0>);
+  static const int new_warps = [] { const char* e = getenv("M3B200_DEC_WARPS2"); return e ? atoi(e) : 16; }();  // 16: 4.58 -> 4.44 ms (r02j, r02m)
+  const bool w16 = new_warps == 16 && p.up_u % 4 == 0;  // 16 epilogue warps: one transposed-conv phase per column group
+  const void* kern = w16 ? (fmt ? reinterpret_cast<const void*>(dec_fused_kernel<1, 16>) : reinterpret_cast<const void*>(dec_fused_kernel<0, 16>))
+                         : (fmt ? reinterpret_cast<const void*>(dec_fused_kernel<1, 8>) : reinterpret_cast<const void*>(dec_fused_kernel<0, 8>));
   ensure_max_dynamic_smem(kern);
   const long long items = (long long)n_seg * p.max_win;
   const int grid = int(items < n_sm ? items : n_sm);
-  if (fmt) dec_fused_kernel<1><<<grid, kThreads, smem, st>>>(p);
-  else dec_fused_kernel<0><<<grid, kThreads, smem, st>>>(p);
+  static const bool want_prof = getenv("M3B200_DEC_PROFILE") != nullptr;
+  static long long* d_prof = nullptr;
+  if (want_prof) {
+    if (!d_prof) cudaMalloc(&d_prof, 16 * sizeof(long long));
+    cudaMemsetAsync(d_prof, 0, 16 * sizeof(long long), st);
+    p.prof = d_prof;
+  }
+  const int threads = 32 * ((w16 ? 16 : 8) + 1 + kLoaders);
+  if (w16) {
+    if (fmt) dec_fused_kernel<1, 16><<<grid, threads, smem, st>>>(p);
+    else dec_fused_kernel<0, 16><<<grid, threads, smem, st>>>(p);
+  } else {
+    if (fmt) dec_fused_kernel<1, 8><<<grid, threads, smem, st>>>(p);
+    else dec_fused_kernel<0, 8><<<grid, threads, smem, st>>>(p);
+  }
   post_launch("dec_fused_kernel", st);
+  if (want_prof) {  // debug only: synchronous read-back of the per-role cycle counters (summed over CTAs)
+    long long h[16];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, d_prof, sizeof h, cudaMemcpyDeviceToHost);
+    const double n = double(h[5] > 0 ? h[5] : 1);
+    fprintf(stderr,
+            "[dec_fused profile] windows %lld grid %d | issuer cycles/window: total %.0f wait_x %.0f wait_y %.0f wait_a %.0f wait_o %.0f | "
+            "epilogue warp 0: total %.0f wait_u %.0f wait_p %.0f wait_c1 %.0f wait_c2 %.0f\n",
+            h[5], grid, h[0] / n, h[1] / n, h[2] / n, h[3] / n, h[4] / n, h[8] / n, h[9] / n, h[10] / n, h[11] / n, h[12] / n);
+  }
 }
 
 }  // namespace m3

@@ -15,7 +15,10 @@
 //   * each WN layer shrinks the exact region by 2 frames per side: windows advance by 128 - 4*nl.
 // The channel Flip between coupling layers is folded into the packing of pre/post weights.
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <stdexcept>
+#include <type_traits>
 
 #include "kernels.h"
 #include "tc_common.cuh"
@@ -59,6 +62,12 @@ __global__ void __launch_bounds__(FL_THREADS, 1) flow_tc_kernel(FlowTcParams p) 
   float* s_pob = s_skb + Hc;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+#ifdef M3B200_KERNEL_PROFILE  // per-role cycle counters (M3B200_FLOW_PROFILE=1); compiled out by default (+5 % kernel time when present)
+  const bool prof = p.prof != nullptr;
+#else
+  constexpr bool prof = false;
+#endif
+  const long long k_start = prof ? clock64() : 0;
   if (warp == 0) tc::tmem_alloc<512>(&tmem_slot);
   if (tid == 32) {
     for (int s = 0; s < FL_STAGES; ++s) {
@@ -124,6 +133,16 @@ __global__ void __launch_bounds__(FL_THREADS, 1) flow_tc_kernel(FlowTcParams p) 
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem = tmem_slot;
+  const long long k_pro = prof ? clock64() : 0;
+  auto timed_wait = [&](uint64_t* bar, uint32_t parity, long long& acc) {
+    if (prof && !tc::mbar_test(bar, parity)) {  // only waits that actually block are timed
+      const long long t = clock64();
+      tc::mbar_wait(bar, parity);
+      acc += clock64() - t;
+    } else {
+      tc::mbar_wait(bar, parity);
+    }
+  };
   const uint32_t T_H = 0, T_SKIP = uint32_t(Hc), T_ACC = 2u * uint32_t(Hc);  // ACC0 / ACC1: +0 / +64
   const int n_gate_chunks = Hc / 32;    // 32 gated channels per chunk (64 MMA columns)
   const int n_h_chunks = Hc / FL_NC;    // 64-column chunks of an Hc-wide output
@@ -134,10 +153,11 @@ __global__ void __launch_bounds__(FL_THREADS, 1) flow_tc_kernel(FlowTcParams p) 
     if (tc::elect_one()) {
       const uint16_t* src = p.w;
       int it = 0;
+      long long w_empty = 0;
       auto push = [&](int K) {
         const int s = it % FL_STAGES;
         const uint32_t bytes = uint32_t(K) * FL_NC * 2;
-        tc::mbar_wait(&empty_bar[s], (((it / FL_STAGES) & 1) ^ 1));
+        timed_wait(&empty_bar[s], (((it / FL_STAGES) & 1) ^ 1), w_empty);
         tc::mbar_expect_tx(&full_bar[s], bytes);
         tc::bulk_g2s(wring + size_t(s) * slot_bytes, src, bytes, &full_bar[s]);
         src += size_t(K) * FL_NC;
@@ -151,63 +171,96 @@ __global__ void __launch_bounds__(FL_THREADS, 1) flow_tc_kernel(FlowTcParams p) 
         for (int c = 0; c < nrs; ++c) push(Hc);                        // res_skip i
       }
       for (int c = 0; c < n_post_chunks; ++c) push(Hc);                // post
+      if (prof) atomicAdd(reinterpret_cast<unsigned long long*>(p.prof + 8), (unsigned long long)w_empty);
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (tc::elect_one()) {
       const uint32_t idesc = tc::make_idesc(128, FL_NC, FMT);
       const uint32_t aH = tc::smem_u32(bufH), aA = tc::smem_u32(bufA);
-      int it = 0;
-      // one weight stage = one (chunk[, tap]) block: K/16 MMAs into `dst`
-      auto stage_mma = [&](uint32_t abase, int rows_pitch, int row0, int K, uint32_t dst, bool first) {
-        const int s = it % FL_STAGES;
-        tc::mbar_wait(&full_bar[s], ((it / FL_STAGES) & 1));
-        tc::fence_after_sync();
-        const uint32_t wbase = tc::smem_u32(wring + size_t(s) * slot_bytes);
-        for (int ks = 0; ks < K / 16; ++ks) {
-          const uint64_t ad = tc::make_desc(abase + uint32_t((ks * 2) * rows_pitch + row0) * 16u, uint32_t(rows_pitch) * 16u, 128u);
-          const uint64_t bd = tc::make_desc(wbase + uint32_t(ks * 2 * FL_NC) * 16u, uint32_t(FL_NC) * 16u, 128u);
+      // one weight stage = one (chunk[, tap]) block: K/16 MMAs into `dst`.  The descriptors of a stage differ only
+      // in their 14-bit start-address field, so the k-steps are fully unrolled around two descriptor templates:
+      // one independent 32-bit add per operand and MMA instead of a shift/mask/or chain on the uniform datapath
+      // (the rolled loop issued one MMA per ~100 cycles -- ncu: 1734 MMAs in 176 k cycles per window -- while
+      // the tensor pipe needs 48.6).
+      const uint32_t a_hiH = uint32_t(tc::make_desc(0u, uint32_t(ROWS_H) * 16u, 128u) >> 32);  // same for both buffers:
+      const uint32_t b_hi = uint32_t(tc::make_desc(0u, uint32_t(FL_NC) * 16u, 128u) >> 32);    // SBO + version bit
+      const uint32_t a_loH = uint32_t(tc::make_desc(aH, uint32_t(ROWS_H) * 16u, 128u));
+      const uint32_t a_loA = uint32_t(tc::make_desc(aA, uint32_t(ROWS_A) * 16u, 128u));
+      uint32_t b_lo[FL_STAGES];
+#pragma unroll
+      for (int s = 0; s < FL_STAGES; ++s)
+        b_lo[s] = uint32_t(tc::make_desc(tc::smem_u32(wring + size_t(s) * slot_bytes), uint32_t(FL_NC) * 16u, 128u));
+      int slot = 0;
+      uint32_t slot_par = 0;
+      long long c_full = 0, c_acc = 0, c_h = 0, c_act = 0;
+      const long long c_start = prof ? clock64() : 0;
+      auto stage_mma = [&](auto ks_tag, uint32_t a_lo, uint32_t a_kstep, uint32_t dst, bool first) {
+        constexpr int KS = decltype(ks_tag)::value;
+        timed_wait(&full_bar[slot], slot_par, c_full);
+        tc::fence_after_sync();  // (measured free: r02l A/B with and without it)
+        const uint32_t bl = slot == 0 ? b_lo[0] : (slot == 1 ? b_lo[1] : b_lo[2]);
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+          const uint64_t ad = (uint64_t(a_hiH) << 32) | uint64_t(a_lo + uint32_t(ks) * a_kstep);
+          const uint64_t bd = (uint64_t(b_hi) << 32) | uint64_t(bl + uint32_t(ks * 2 * FL_NC));
           tc::mma_f16_ss(tmem + dst, ad, bd, idesc, (first && ks == 0) ? 0u : 1u);
         }
-        tc::mma_commit(&empty_bar[s]);
-        ++it;
+        tc::mma_commit(&empty_bar[slot]);
+        if (++slot == FL_STAGES) {
+          slot = 0;
+          slot_par ^= 1u;
+        }
       };
+      using KX6 = std::integral_constant<int, 6>;
+      using KH12 = std::integral_constant<int, 12>;
+      const uint32_t kstepH = uint32_t(2 * ROWS_H), kstepA = uint32_t(2 * ROWS_A);
       uint32_t ph_hready = 0, ph_act = 0;
       int acc_it = 0;
       // ---- pre: H = x0 . Wpre ----
-      for (int c = 0; c < n_h_chunks; ++c) stage_mma(aA, ROWS_A, 0, half, T_H + c * FL_NC, true);
+      for (int c = 0; c < n_h_chunks; ++c) stage_mma(KX6{}, a_loA, kstepA, T_H + c * FL_NC, true);
       tc::mma_commit(&h_full);
       for (int i = 0; i < nl; ++i) {
         // ---- in_layer i: gate chunks into ACC ping-pong; needs the fp16 h of this layer ----
-        tc::mbar_wait(&h_ready, ph_hready);
+        timed_wait(&h_ready, ph_hready, c_h);
         ph_hready ^= 1u;
         tc::fence_after_sync();
         for (int c = 0; c < n_gate_chunks; ++c, ++acc_it) {
           const int b = acc_it & 1;
-          tc::mbar_wait(&acc_empty[b], (((acc_it >> 1) & 1) ^ 1));
+          timed_wait(&acc_empty[b], (((acc_it >> 1) & 1) ^ 1), c_acc);
           tc::fence_after_sync();
-          for (int tap = 0; tap < 5; ++tap) stage_mma(aH, ROWS_H, tap, Hc, T_ACC + b * FL_NC, tap == 0);
+          for (int tap = 0; tap < 5; ++tap) stage_mma(KH12{}, a_loH + uint32_t(tap), kstepH, T_ACC + b * FL_NC, tap == 0);
           tc::mma_commit(&acc_full[b]);
         }
         // ---- res_skip i: accumulate straight into H / SKIP; needs the whole fp16 act ----
-        tc::mbar_wait(&act_ready, ph_act);
+        timed_wait(&act_ready, ph_act, c_act);
         ph_act ^= 1u;
         tc::fence_after_sync();
         if (i < nl - 1)
-          for (int c = 0; c < n_h_chunks; ++c) stage_mma(aA, ROWS_A, 0, Hc, T_H + c * FL_NC, false);
-        for (int c = 0; c < n_h_chunks; ++c) stage_mma(aA, ROWS_A, 0, Hc, T_SKIP + c * FL_NC, i == 0);
+          for (int c = 0; c < n_h_chunks; ++c) stage_mma(KH12{}, a_loA, kstepA, T_H + c * FL_NC, false);
+        for (int c = 0; c < n_h_chunks; ++c) stage_mma(KH12{}, a_loA, kstepA, T_SKIP + c * FL_NC, i == 0);
         tc::mma_commit(&h_full);
       }
       // ---- post: m = skip . Wpost (fp16 skip staged in bufA by the epilogue) ----
-      tc::mbar_wait(&act_ready, ph_act);
+      timed_wait(&act_ready, ph_act, c_act);
       ph_act ^= 1u;
       tc::fence_after_sync();
       for (int c = 0; c < n_post_chunks; ++c, ++acc_it) {
         const int b = acc_it & 1;
         tc::mbar_wait(&acc_empty[b], (((acc_it >> 1) & 1) ^ 1));
         tc::fence_after_sync();
-        stage_mma(aA, ROWS_A, 0, Hc, T_ACC + b * FL_NC, true);
+        stage_mma(KH12{}, a_loA, kstepA, T_ACC + b * FL_NC, true);
         tc::mma_commit(&acc_full[b]);
+      }
+      if (prof) {
+        unsigned long long* q = reinterpret_cast<unsigned long long*>(p.prof);
+        atomicAdd(q + 0, (unsigned long long)(clock64() - c_start));
+        atomicAdd(q + 1, (unsigned long long)c_full);
+        atomicAdd(q + 2, (unsigned long long)c_acc);
+        atomicAdd(q + 3, (unsigned long long)c_h);
+        atomicAdd(q + 4, (unsigned long long)c_act);
+        atomicAdd(q + 5, 1ull);
+        atomicAdd(q + 6, (unsigned long long)(k_pro - k_start));
       }
     }
   } else {
@@ -220,10 +273,13 @@ __global__ void __launch_bounds__(FL_THREADS, 1) flow_tc_kernel(FlowTcParams p) 
     const bool inside = g >= 0 && g < L;
     uint32_t ph_hfull = 0;
     int acc_it = 0;
+    long long e_h = 0, e_acc = 0;
     const int hcols = Hc / 2;          // columns of H / SKIP per thread
 
     // TMEM region (Hc fp32 columns) + bias -> masked 16-bit A operand rows in `dst`
     auto region_to_smem = [&](uint32_t region, const float* bias, uint8_t* dst, int pitch, int row_off) {
+      // (two loads per tcgen05.wait::ld; putting all six of a thread's loads in flight was tried on the decoder
+      // kernels and made them slower, r02k)
       for (int cc = 0; cc < hcols; cc += 32) {
         __syncwarp();
         float v0[16], v1[16];
@@ -251,7 +307,7 @@ __global__ void __launch_bounds__(FL_THREADS, 1) flow_tc_kernel(FlowTcParams p) 
 
     for (int i = 0; i < nl; ++i) {
       // ---- h of layer i (pre or previous res update) -> bufH ----
-      tc::mbar_wait(&h_full, ph_hfull);
+      timed_wait(&h_full, ph_hfull, e_h);
       ph_hfull ^= 1u;
       tc::fence_after_sync();
       region_to_smem(T_H, s_cb + i * Hc, bufH, ROWS_H, 2);
@@ -259,7 +315,7 @@ __global__ void __launch_bounds__(FL_THREADS, 1) flow_tc_kernel(FlowTcParams p) 
       // ---- gate chunks -> bufA ----
       for (int c = 0; c < n_gate_chunks; ++c, ++acc_it) {
         const int b = acc_it & 1;
-        tc::mbar_wait(&acc_full[b], ((acc_it >> 1) & 1));
+        timed_wait(&acc_full[b], ((acc_it >> 1) & 1), e_acc);
         tc::fence_after_sync();
         float va[16], vb[16];
         const int j0 = hh * 16;
@@ -289,7 +345,7 @@ __global__ void __launch_bounds__(FL_THREADS, 1) flow_tc_kernel(FlowTcParams p) 
       if (lane == 0) tc::mbar_arrive(&act_ready);
     }
     // ---- skip -> bufA (A operand of post) ----
-    tc::mbar_wait(&h_full, ph_hfull);
+    timed_wait(&h_full, ph_hfull, e_h);
     ph_hfull ^= 1u;
     tc::fence_after_sync();
     region_to_smem(T_SKIP, s_skb, bufA, ROWS_A, 0);
@@ -329,10 +385,17 @@ __global__ void __launch_bounds__(FL_THREADS, 1) flow_tc_kernel(FlowTcParams p) 
         }
       }
     }
+    if (prof && warp == 2 && lane == 0) {
+      unsigned long long* q = reinterpret_cast<unsigned long long*>(p.prof);
+      atomicAdd(q + 9, (unsigned long long)(clock64() - k_pro));   // epilogue warp: whole window after the prologue
+      atomicAdd(q + 10, (unsigned long long)e_h);
+      atomicAdd(q + 11, (unsigned long long)e_acc);
+    }
   }
   tc::fence_before_sync();
   __syncthreads();
   if (warp == 0) tc::tmem_dealloc<512>(tmem);
+  if (prof && tid == 0) atomicAdd(reinterpret_cast<unsigned long long*>(p.prof + 7), (unsigned long long)(clock64() - k_start));
 }
 
 size_t flow_tc_smem_bytes(int Hc, int half, int nl) {
@@ -345,7 +408,7 @@ size_t flow_tc_smem_bytes(int Hc, int half, int nl) {
 
 bool flow_tc_supported(int Hc, int half, int nl, int kernel) {
   if (kernel != 5 || nl < 1 || nl > 8) return false;
-  if (Hc % 64 || half % 16 || half > Hc) return false;
+  if (Hc != 192 || half != 96) return false;  // the issuer's k-step loops are unrolled for these (every shipped voice)
   if (2 * Hc + 2 * FL_NC > 512) return false;  // TMEM: H + SKIP + two accumulators
   if (128 - 4 * nl < 32) return false;
   return flow_tc_smem_bytes(Hc, half, nl) <= size_t(225 * 1024);
@@ -357,9 +420,28 @@ void launch_flow_tc(const FlowTcParams& p, int fmt, int n_seg, int max_len, cuda
   ensure_max_dynamic_smem(fmt ? reinterpret_cast<const void*>(flow_tc_kernel<1>) : reinterpret_cast<const void*>(flow_tc_kernel<0>));
   const int stride = 128 - 4 * p.nl;
   dim3 grid((max_len + stride - 1) / stride, n_seg);
-  if (fmt) flow_tc_kernel<1><<<grid, FL_THREADS, smem, st>>>(p);
-  else flow_tc_kernel<0><<<grid, FL_THREADS, smem, st>>>(p);
+  static const bool want_prof = getenv("M3B200_FLOW_PROFILE") != nullptr;
+  static long long* d_prof = nullptr;
+  FlowTcParams q = p;
+  if (want_prof) {
+    if (!d_prof) cudaMalloc(&d_prof, 16 * sizeof(long long));
+    cudaMemsetAsync(d_prof, 0, 16 * sizeof(long long), st);
+    q.prof = d_prof;
+  }
+  if (fmt) flow_tc_kernel<1><<<grid, FL_THREADS, smem, st>>>(q);
+  else flow_tc_kernel<0><<<grid, FL_THREADS, smem, st>>>(q);
   post_launch("flow_tc_kernel", st);
+  if (want_prof) {  // debug only: synchronous read-back of the per-role cycle counters (summed over windows)
+    long long h[16];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, d_prof, sizeof h, cudaMemcpyDeviceToHost);
+    const double n = double(h[5] > 0 ? h[5] : 1);
+    fprintf(stderr,
+            "[flow profile] windows %lld | CTA cycles %.0f (prologue %.0f) | issuer: total %.0f wait_weights %.0f wait_acc_empty %.0f "
+            "wait_h_ready %.0f wait_act_ready %.0f | producer wait_empty %.0f | epilogue warp: total %.0f wait_h_full %.0f "
+            "wait_acc_full %.0f\n",
+            h[5], h[7] / n, h[6] / n, h[0] / n, h[1] / n, h[2] / n, h[3] / n, h[4] / n, h[8] / n, h[9] / n, h[10] / n, h[11] / n);
+  }
 }
 
 }  // namespace m3

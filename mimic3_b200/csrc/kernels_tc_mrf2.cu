@@ -21,13 +21,24 @@
 
 namespace m3 {
 
+// per-role cycle counters (M3B200_MRF_PROFILE=1) exist only in builds made with M3B200_KERNEL_PROFILE=1 in the
+// environment of `python -m mimic3_b200.build`: merely compiled in they cost the persistent kernels 5-9 %
+#ifdef M3B200_KERNEL_PROFILE
+#define M3_PROF(p) ((p).prof != nullptr)
+#else
+#define M3_PROF(p) false
+#endif
+
 namespace {
 constexpr int wC = 64, wNT = 2, wR = wNT * 128, wCH = wC / 8, wKS = wC / 16;
-constexpr int wEpiWarps = 8, wIssuer = 8, wIssuers = wNT, wLoader = wIssuer + wIssuers, wThreads = 32 * (wLoader + 1);
+constexpr int wIssuers = wNT;  // epilogue warps NEW (8 or 16) come first, then the issuers, then the weight loader
 constexpr int wSegTable = 1024;  // per-utterance row counts cached in shared memory (larger batches read global memory)
 constexpr uint32_t wTapBytes = wC * wC * 2;
+constexpr int wStageTaps = 2;  // taps per ring slot / issuer stage: every stage costs the issuing thread a wait and a
+                               // tcgen05.commit (~140 cycles, m3_selftest 501-560) on top of its 4 MMAs per tap
+constexpr uint32_t wSlotBytes = wStageTaps * wTapBytes;
 constexpr uint32_t wS0 = 384;
-constexpr int wMaxSlots = 12;
+constexpr int wMaxSlots = 6;
 enum WBar { WX_READY = 0, WC1_DONE, WY_READY = WC1_DONE + 3, WC2_DONE = WY_READY + 3, WF_DONE, WFULL, WEMPTY = WFULL + wMaxSlots, WNBAR = WEMPTY + wMaxSlots };
 
 struct WGeo {
@@ -39,7 +50,7 @@ __host__ __device__ inline WGeo make_wgeo(const MrfParams& p, int nslot) {
   g.rows_x = (wR + 2 * p.HX) | 1;
   size_t o = 0;
   g.off_ring = o;
-  o += size_t(nslot) * wTapBytes;
+  o += size_t(nslot) * wSlotBytes;
   g.off_x = o;
   o += size_t(wCH) * g.rows_x * 16;
   for (int j = 0; j < 3; ++j) {
@@ -61,9 +72,14 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 __device__ __forceinline__ int chain_at(int win, int pos) { return (win + pos) % 3; }
 }  // namespace
 
-template <int FMT>
-__global__ void __launch_bounds__(wThreads, 1) mrf_ws_kernel(MrfParams p) {
+// NEW = epilogue warps: 8 (each thread owns 32 channels of its rows) or 16 (16 channels: half the dependent
+// tmem_ld -> math -> st.shared chain per thread and twice the warps to hide it -- the M3B200_MRF_PROFILE counters show
+// the epilogue warps, not the tensor pipe, are the busiest resource of this kernel)
+template <int FMT, int NEW>
+__global__ void __maxnreg__(NEW == 16 ? 96 : 168) mrf_ws_kernel(MrfParams p) {  // 19 warps x 96 x 32 registers fit one SM
   using E = tc::Elem<FMT>;
+  constexpr int wEpiWarps = NEW, wIssuer = NEW, wLoader = wIssuer + wIssuers, wThreads = 32 * (wLoader + 1);
+  constexpr int NCG = NEW / 4, HC = wC / NCG, NH = HC / 16;  // column groups, channels and 16-channel halves per thread
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(8) uint64_t bars[WNBAR];
@@ -127,8 +143,9 @@ __global__ void __launch_bounds__(wThreads, 1) mrf_ws_kernel(MrfParams p) {
           for (int jj = 0; jj < 3; ++jj) {
             const int j = chain_at(win, jj);
             const uint16_t* src = p.w16 + p.woff[j][d];
-            for (int t = 0; t < p.k[j]; ++t) {
-              if (p.prof && !tc::mbar_test(&bars[WEMPTY + slot], eparity)) {
+            for (int t = 0; t < p.k[j]; t += wStageTaps) {
+              const uint32_t bytes = uint32_t(p.k[j] - t < wStageTaps ? p.k[j] - t : wStageTaps) * wTapBytes;
+              if (M3_PROF(p) && !tc::mbar_test(&bars[WEMPTY + slot], eparity)) {
                 const long long t0 = clock64();
                 tc::mbar_wait(&bars[WEMPTY + slot], eparity);
                 l_empty += clock64() - t0;
@@ -136,8 +153,8 @@ __global__ void __launch_bounds__(wThreads, 1) mrf_ws_kernel(MrfParams p) {
               } else {
                 tc::mbar_wait(&bars[WEMPTY + slot], eparity);
               }
-              tc::mbar_expect_tx(&bars[WFULL + slot], wTapBytes);
-              tc::bulk_g2s(ring + size_t(slot) * wTapBytes, src + size_t(t) * wC * wC, wTapBytes, &bars[WFULL + slot]);
+              tc::mbar_expect_tx(&bars[WFULL + slot], bytes);
+              tc::bulk_g2s(ring + size_t(slot) * wSlotBytes, src + size_t(t) * wC * wC, bytes, &bars[WFULL + slot]);
               if (++slot == uint32_t(nslot)) {
                 slot = 0;
                 eparity ^= 1u;
@@ -145,7 +162,7 @@ __global__ void __launch_bounds__(wThreads, 1) mrf_ws_kernel(MrfParams p) {
             }
           }
       }
-      if (p.prof) {
+      if (M3_PROF(p)) {
         atomicAdd(reinterpret_cast<unsigned long long*>(p.prof + 14), (unsigned long long)l_empty);
         atomicAdd(reinterpret_cast<unsigned long long*>(p.prof + 15), (unsigned long long)l_blocked);
       }
@@ -165,7 +182,7 @@ __global__ void __launch_bounds__(wThreads, 1) mrf_ws_kernel(MrfParams p) {
       const int my_tile = warp - wIssuer;
       uint32_t slot = 0, fparity = 0u;
       long long c_full = 0, c_x = 0, c_y = 0, c_f = 0;
-      const bool prof = p.prof != nullptr;
+      const bool prof = M3_PROF(p);
       const long long c_start = clock64();
       long long n_blocked = 0;
       auto timed_wait = [&](uint64_t* bar, uint32_t parity, long long& acc) {
@@ -185,16 +202,23 @@ __global__ void __launch_bounds__(wThreads, 1) mrf_ws_kernel(MrfParams p) {
         uint32_t at = uint32_t(a_tmpl) + uint32_t(halo - ((k - 1) / 2) * dil);
         const uint32_t kstep = uint32_t(2 * rows_in);
 #pragma unroll 1
-        for (int t = 0; t < k; ++t, at += uint32_t(dil)) {
+        for (int t = 0; t < k; t += wStageTaps) {
           timed_wait(&bars[WFULL + slot], fparity, c_full);
-          tc::fence_after_sync();
-          const uint32_t bt = b_lo0 + slot * (wTapBytes >> 4);
+          tc::fence_after_sync();  // (measured free: r02l A/B with and without it)
+          const uint32_t bt0 = b_lo0 + slot * (wSlotBytes >> 4);
 #pragma unroll
-          for (int ks = 0; ks < wKS; ++ks) {
-            const uint64_t bd = (uint64_t(b_hi) << 32) | uint64_t(bt + uint32_t(ks * 2 * wC));
-            const uint32_t acc = (ks > 0 || acc0 || t > 0) ? 1u : 0u;
-            const uint64_t ad = (uint64_t(a_hi) << 32) | uint64_t(at + uint32_t(ks) * kstep + uint32_t(my_tile * 128));
-            tc::mma_f16_ss(tmem + dcol + uint32_t(my_tile * wC), ad, bd, idesc, acc);
+          for (int tt = 0; tt < wStageTaps; ++tt) {
+            if (t + tt < k) {
+              const uint32_t bt = bt0 + uint32_t(tt) * (wTapBytes >> 4);
+#pragma unroll
+              for (int ks = 0; ks < wKS; ++ks) {
+                const uint64_t bd = (uint64_t(b_hi) << 32) | uint64_t(bt + uint32_t(ks * 2 * wC));
+                const uint32_t acc = (ks > 0 || acc0 || t + tt > 0) ? 1u : 0u;
+                const uint64_t ad = (uint64_t(a_hi) << 32) | uint64_t(at + uint32_t(ks) * kstep + uint32_t(my_tile * 128));
+                tc::mma_f16_ss(tmem + dcol + uint32_t(my_tile * wC), ad, bd, idesc, acc);
+              }
+              at += uint32_t(dil);
+            }
           }
           tc::mma_commit(&bars[WEMPTY + slot]);
           if (++slot == uint32_t(nslot)) {
@@ -240,10 +264,10 @@ __global__ void __launch_bounds__(wThreads, 1) mrf_ws_kernel(MrfParams p) {
   } else {
     // =================================== epilogue warps ===========================================
     // warp w: TMEM lane quarter q = w & 3 (hardware restriction), channel half hh = w >> 2 (32 channels)
-    const int q = warp & 3, hh = warp >> 2;
+    const int q = warp & 3, cg = warp >> 2;
     const uint32_t lane_base = tmem + (uint32_t(q * 32) << 16);
-    const int col0 = hh * 32;
-    float xr[wNT][32];  // this thread's x (fp32 residual source): rows {m*128 + q*32 + lane}, 32 channels
+    const int col0 = cg * HC;
+    float xr[wNT][HC];  // this thread's x (fp32 residual source): rows {m*128 + q*32 + lane}, HC channels
 
     auto arrive = [&](int b) {
       tc::fence_async_smem();
@@ -262,7 +286,7 @@ __global__ void __launch_bounds__(wThreads, 1) mrf_ws_kernel(MrfParams p) {
           pk.z = E::pack2(wlrelu(v[8 * c8 + 4], 0.1f), wlrelu(v[8 * c8 + 5], 0.1f));
           pk.w = E::pack2(wlrelu(v[8 * c8 + 6], 0.1f), wlrelu(v[8 * c8 + 7], 0.1f));
         }
-        *reinterpret_cast<uint4*>(buf + (size_t(hh * 4 + h * 2 + c8) * pitch + row) * 16) = pk;
+        *reinterpret_cast<uint4*>(buf + (size_t(col0 / 8 + h * 2 + c8) * pitch + row) * 16) = pk;
       }
     };
     // fetch the window's x: own rows into registers (fp32 residual) and, as lrelu -> 16-bit, into bufX
@@ -278,10 +302,10 @@ __global__ void __launch_bounds__(wThreads, 1) mrf_ws_kernel(MrfParams p) {
         const float* src = p.x + (base + gi) * wC + col0;
         if (gi >= 0 && gi < L) {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) ldg256(src + 8 * e, &xr[m][8 * e]);
+          for (int e = 0; e < HC / 8; ++e) ldg256(src + 8 * e, &xr[m][8 * e]);
         } else {
 #pragma unroll
-          for (int e = 0; e < 32; ++e) xr[m][e] = 0.f;
+          for (int e = 0; e < HC; ++e) xr[m][e] = 0.f;
         }
       }
       float hv[8];
@@ -300,8 +324,8 @@ __global__ void __launch_bounds__(wThreads, 1) mrf_ws_kernel(MrfParams p) {
       for (int m = 0; m < wNT; ++m) {
         const int r = m * 128 + q * 32 + lane;
         const int gi = w0 + r;
-        store_ops(bufX, g.rows_x, r + p.HX, 0, xr[m], gi >= 0 && gi < L);
-        store_ops(bufX, g.rows_x, r + p.HX, 1, xr[m] + 16, gi >= 0 && gi < L);
+#pragma unroll
+        for (int h = 0; h < NH; ++h) store_ops(bufX, g.rows_x, r + p.HX, h, xr[m] + 16 * h, gi >= 0 && gi < L);
       }
       if (has_halo) {
         uint4 pk = make_uint4(0u, 0u, 0u, 0u);
@@ -327,9 +351,20 @@ __global__ void __launch_bounds__(wThreads, 1) mrf_ws_kernel(MrfParams p) {
       }
     };
 
-    const bool prof = p.prof != nullptr && tid == 0;
-    long long e_c1w = 0, e_c1 = 0, e_lx = 0, e_c2w = 0, e_fin = 0, e_t = 0;
-    const long long e_start = clock64();
+    // profile counters of thread 0 live in shared memory (seven 64-bit registers per epilogue thread would spill)
+    const bool prof = M3_PROF(p) && tid == 0;
+    __shared__ long long s_prof[8];
+    long long& e_c1w = s_prof[0];
+    long long& e_c1 = s_prof[1];
+    long long& e_lx = s_prof[2];
+    long long& e_c2w = s_prof[3];
+    long long& e_fin = s_prof[4];
+    long long& e_t = s_prof[5];
+    long long& e_start = s_prof[6];
+    if (prof) {
+      e_c1w = e_c1 = e_lx = e_c2w = e_fin = e_t = 0;
+      e_start = clock64();
+    }
     if (first < total) {
       load_x(first);
       arrive(WX_READY);
@@ -371,7 +406,7 @@ __global__ void __launch_bounds__(wThreads, 1) mrf_ws_kernel(MrfParams p) {
           const int gi = w0 + r;
           const bool inside = gi >= 0 && gi < L;
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
+          for (int h = 0; h < NH; ++h) {
             float v[16], acc[16];
             tc::tmem_ld16(lane_base + uint32_t(j * 128 + m * wC + col0 + 16 * h), v);
             if (jj > 0) tc::tmem_ld16(lane_base + uint32_t(j0 * 128 + m * wC + col0 + 16 * h), acc);
@@ -425,12 +460,12 @@ __global__ void __launch_bounds__(wThreads, 1) mrf_ws_kernel(MrfParams p) {
           const bool store = r >= p.H && r < wR - p.H && gi < L;
           float* dst = p.out + (base + gi) * wC + col0;
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
+          for (int h = 0; h < NH; ++h) {
             float v[16], acc[16];
             tc::tmem_ld16(lane_base + wS0 + uint32_t(m * wC + col0 + 16 * h), v);
             tc::tmem_ld16(lane_base + uint32_t(park * 128 + m * wC + col0 + 16 * h), acc);
             tc::tmem_ld_wait();
-            if (m == wNT - 1 && h == 1) {  // the parked sum and S are consumed
+            if (m == wNT - 1 && h == NH - 1) {  // the parked sum and S are consumed
               tc::fence_before_sync();
               __syncwarp();
               if (lane == 0) tc::mbar_arrive(&bars[WF_DONE]);
@@ -473,8 +508,8 @@ static int mrf_ws_slots(const MrfParams& p, size_t* smem_out) {
   cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
   const size_t budget = size_t(optin) - 2048 - 4 * wSegTable - 128;  // static shared memory (barriers, biases, row table) + alignment
   const WGeo g0 = make_wgeo(p, 0);
-  if (g0.total + 4 * wTapBytes > budget) return 0;
-  int n = int((budget - g0.total) / wTapBytes);
+  if (g0.total + 3 * wSlotBytes > budget) return 0;
+  int n = int((budget - g0.total) / wSlotBytes);
   if (n > wMaxSlots) n = wMaxSlots;
   if (smem_out) *smem_out = make_wgeo(p, n).total + 128;
   return n;
@@ -484,13 +519,14 @@ bool mrf_ws_supported(const MrfParams& p, int C) {
   if (C != wC || p.nk != 3 || p.nd != 2) return false;
   for (int j = 0; j < 3; ++j)
     if (p.k[j] < 1 || p.k[j] > 11 || !(p.k[j] & 1)) return false;
-  if (2 * p.HX * wCH > wEpiWarps * 32) return false;  // halo items: one per epilogue thread
+  if (2 * p.HX * wCH > 8 * 32) return false;  // halo items: one per epilogue thread (8 or 16 epilogue warps)
   if (wR - 2 * p.H < 64) return false;
-  return mrf_ws_slots(p, nullptr) >= 4;
+  return mrf_ws_slots(p, nullptr) >= 3;
 }
 
 void launch_mrf_ws(const MrfParams& p_in, int fmt, int n_seg, int max_len, cudaStream_t st) {
   MrfParams p = p_in;
+
   p.stride = wR - 2 * p.H;
   const int L = max_len * p.scale;
   p.n_seg = n_seg;
@@ -498,14 +534,17 @@ void launch_mrf_ws(const MrfParams& p_in, int fmt, int n_seg, int max_len, cudaS
   if (p.max_win <= 0 || n_seg <= 0) return;
   size_t smem = 0;
   p.nslot = mrf_ws_slots(p, &smem);
-  if (p.nslot < 4) throw std::runtime_error("mrf_ws: shared memory budget");
+  if (p.nslot < 3) throw std::runtime_error("mrf_ws: shared memory budget");
   static const int n_sm = [] {
     int dev = 0, n = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     return n;
   }();
-  const void* kern = fmt ? reinterpret_cast<const void*>(mrf_ws_kernel<1>) : reinterpret_cast<const void*>(mrf_ws_kernel<0>);
+  static const int new_warps = [] { const char* e = getenv("M3B200_MRF64_WARPS"); return e ? atoi(e) : 8; }();
+  const bool w16 = new_warps == 16;
+  const void* kern = w16 ? (fmt ? reinterpret_cast<const void*>(mrf_ws_kernel<1, 16>) : reinterpret_cast<const void*>(mrf_ws_kernel<0, 16>))
+                         : (fmt ? reinterpret_cast<const void*>(mrf_ws_kernel<1, 8>) : reinterpret_cast<const void*>(mrf_ws_kernel<0, 8>));
   ensure_max_dynamic_smem(kern);
   const long long items = (long long)n_seg * p.max_win;
   const int grid = int(items < n_sm ? items : n_sm);
@@ -516,8 +555,14 @@ void launch_mrf_ws(const MrfParams& p_in, int fmt, int n_seg, int max_len, cudaS
     cudaMemsetAsync(d_prof, 0, 16 * sizeof(long long), st);
     p.prof = d_prof;
   }
-  if (fmt) mrf_ws_kernel<1><<<grid, wThreads, smem, st>>>(p);
-  else mrf_ws_kernel<0><<<grid, wThreads, smem, st>>>(p);
+  const int threads = 32 * ((w16 ? 16 : 8) + wIssuers + 1);
+  if (w16) {
+    if (fmt) mrf_ws_kernel<1, 16><<<grid, threads, smem, st>>>(p);
+    else mrf_ws_kernel<0, 16><<<grid, threads, smem, st>>>(p);
+  } else {
+    if (fmt) mrf_ws_kernel<1, 8><<<grid, threads, smem, st>>>(p);
+    else mrf_ws_kernel<0, 8><<<grid, threads, smem, st>>>(p);
+  }
   post_launch("mrf_ws_kernel", st);
   if (want_prof) {  // debug only: synchronous read-back of the per-role cycle counters (summed over CTAs)
     long long h[16];

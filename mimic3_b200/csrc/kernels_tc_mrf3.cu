@@ -161,7 +161,7 @@ __global__ void __launch_bounds__((NEW + 3) * 32, 1) mrf_ws128_kernel(MrfParams 
 #pragma unroll
           for (int hf = 0; hf < 2; ++hf) {
             tc::mbar_wait(&bars[BFULL + slot], fparity);
-            tc::fence_after_sync();
+            tc::fence_after_sync();  // (measured free: r02l A/B with and without it)
             const uint32_t bt = b_lo0 + slot * (bSlotBytes >> 4);
 #pragma unroll
             for (int ks = 0; ks < bKS / 2; ++ks) {
@@ -408,6 +408,7 @@ bool mrf_ws128_supported(const MrfParams& p, int C) {
 
 void launch_mrf_ws128(const MrfParams& p_in, int fmt, int n_seg, int max_len, cudaStream_t st) {
   MrfParams p = p_in;
+
   p.stride = bR - 2 * p.H;
   const int L = max_len * p.scale;
   p.n_seg = n_seg;

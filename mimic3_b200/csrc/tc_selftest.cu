@@ -154,7 +154,7 @@ double run_probe(int fmt, int K, int N, int taps, int dil, bool with_init, bool 
 // for sm_100a -- TMEM ld/st rate, SS-mode MMA rate for small N, commit->mbarrier latency.
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) tc_ubench_kernel(int mode, int N, int reps, int warps_active,
-                                                        long long* out) {
+                                                        long long* out, const uint8_t* gsrc) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(8) uint64_t bar;
@@ -249,6 +249,177 @@ __global__ void __launch_bounds__(256) tc_ubench_kernel(int mode, int N, int rep
     __syncthreads();
     t0 = 0;
     t1 = 0;
+  } else if (mode == 10) {
+    // What a conv-by-descriptor-shift kernel really issues: `warps_active` is a bit mask of deviations from the
+    // idealised stream of modes 7-9 (same aligned operands every time):
+    //   1: A starts one row (16 B) into its first core matrix    2: odd row pitch (LBO = 133 rows)
+    //   4: four different A start rows (0, 3, 6, 9) round robin   8: four different B blocks round robin
+    //  16: warps 1-4 stream 128-bit STS/LDS on another region    32: warp 5 streams 8 KB bulk copies into smem
+    //  64: A starts half a core matrix (64 B) in
+    const int var = warps_active;
+    __shared__ volatile int stop_flag;
+    __shared__ __align__(8) uint64_t bbar;
+    if (tid == 0) {
+      stop_flag = 0;
+      tc::mbar_init(&bbar, 1);
+      tc::mbar_fence_init();
+    }
+    const uint32_t pitch = (var & 2) ? 133u : 128u;
+    const uint32_t idesc = tc::make_idesc(128, N, 0);
+    const uint32_t a0 = tc::smem_u32(smem) + ((var & 1) ? 16u : 0u) + ((var & 64) ? 64u : 0u);
+    uint64_t ad[4], bd[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      ad[u] = tc::make_desc(a0 + ((var & 4) ? uint32_t(u * 3 * 16) : 0u), pitch * 16u, 128u);
+      bd[u] = tc::make_desc(tc::smem_u32(smem) + 16384u + ((var & 8) ? uint32_t(u * N * 32) : 0u), uint32_t(N) * 16u, 128u);
+    }
+    __syncthreads();
+    if (warp == 0) {
+      if (tc::elect_one()) {
+        const long long e0 = clock64();
+        for (int r = 0; r < reps; r += 4) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) tc::mma_f16_ss(tmem + uint32_t(u * 128), ad[u], bd[u], idesc, r ? 1u : 0u);
+        }
+        tc::mma_commit(&bar);
+        tc::mbar_wait(&bar, 0);
+        out[1] = clock64() - e0;
+        stop_flag = 1;
+      }
+      __syncwarp();
+    } else if ((var & 16) && warp >= 1 && warp <= 4) {
+      uint4* region = reinterpret_cast<uint4*>(smem + 40960) + (warp - 1) * 256 + (tid & 31);
+      uint4 x = make_uint4(tid, 1u, 2u, 3u);
+      while (!stop_flag) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) region[i * 32] = x;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) x.x += region[i * 32].y;
+      }
+      if (x.x == 0x12345u) out[62] = 1;
+    } else if ((var & 32) && warp == 5) {
+      if (tc::elect_one()) {
+        uint32_t ph = 0;
+        while (!stop_flag) {
+          tc::mbar_expect_tx(&bbar, 8192u);
+          tc::bulk_g2s(smem + 57344, gsrc, 8192u, &bbar);
+          tc::mbar_wait(&bbar, ph);
+          ph ^= 1u;
+        }
+      }
+      __syncwarp();
+    }
+    __syncthreads();
+    t0 = 0;
+    t1 = 0;
+  } else if (mode == 11 || mode == 12) {
+    // the per-stage pattern of the streaming kernels: `warps_active` MMAs, then tcgen05.commit to an mbarrier
+    // (mode 12: plus a try_wait on an mbarrier whose phase is already complete and tcgen05.fence::after_thread_sync,
+    // i.e. the "weights have landed" check that precedes every stage)
+    const int period = warps_active > 0 ? warps_active : 12;
+    __shared__ __align__(8) uint64_t cbar[2];
+    if (tid == 0) {
+      tc::mbar_init(&cbar[0], 1);
+      tc::mbar_init(&cbar[1], 1);
+      tc::mbar_fence_init();
+    }
+    const uint32_t idesc = tc::make_idesc(128, N, 0);
+    const uint32_t a0 = tc::smem_u32(smem) + 16u, b0 = tc::smem_u32(smem) + 16384u;
+    __syncthreads();
+    if (tid == 0) tc::mbar_arrive(&cbar[1]);  // phase 0 of cbar[1] is complete from now on
+    __syncthreads();
+    if (warp == 0) {
+      if (tc::elect_one()) {
+        uint64_t ad4[4], bd4[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          ad4[u] = tc::make_desc(a0 + uint32_t(u) * 48u, 133u * 16u, 128u);
+          bd4[u] = tc::make_desc(b0 + uint32_t(u) * uint32_t(N) * 32u, uint32_t(N) * 16u, 128u);
+        }
+        int stage = 0;
+        const long long e0 = clock64();
+        for (int r = 0; r < reps; r += period) {
+          if (mode == 12) {
+            tc::mbar_wait(&cbar[1], 0u);
+            tc::fence_after_sync();
+          }
+          const uint32_t dcol = tmem + uint32_t(stage++ & 3) * 128u;
+          for (int u = 0; u < period; ++u) {
+            const int w = u & 3;
+            const uint64_t ad = w == 0 ? ad4[0] : w == 1 ? ad4[1] : w == 2 ? ad4[2] : ad4[3];
+            const uint64_t bd = w == 0 ? bd4[0] : w == 1 ? bd4[1] : w == 2 ? bd4[2] : bd4[3];
+            tc::mma_f16_ss(dcol, ad, bd, idesc, (r | u) ? 1u : 0u);
+          }
+          tc::mma_commit(&cbar[0]);
+        }
+        tc::mma_commit(&bar);
+        tc::mbar_wait(&bar, 0);
+        out[1] = clock64() - e0;
+      }
+      __syncwarp();
+    }
+    __syncthreads();
+    t0 = 0;
+    t1 = 0;
+  } else if (mode == 13) {
+    // epilogue-style TMEM reads (warps 1-7, three x16 loads per round) with or without a concurrent MMA stream (warp 0):
+    // warps_active bit 0: all three loads before ONE tcgen05.wait::ld (else a wait after each load);
+    // bit 1: warp 0 streams N-column MMAs into columns [256, 512) meanwhile.  Result: cycles per round.
+    const int var = warps_active;
+    __shared__ volatile int stop13;
+    if (tid == 0) stop13 = 0;
+    const uint32_t idesc = tc::make_idesc(128, N, 0);
+    const uint64_t ad = tc::make_desc(tc::smem_u32(smem) + 16u, 133u * 16u, 128u);
+    const uint64_t bd = tc::make_desc(tc::smem_u32(smem) + 16384u, uint32_t(N) * 16u, 128u);
+    __syncthreads();
+    if (warp == 0) {
+      if ((var & 2) && tc::elect_one()) {
+        long long n = 0;
+        while (!stop13) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) tc::mma_f16_ss(tmem + 256u + uint32_t(u & 1) * 128u, ad, bd, idesc, 1u);
+          tc::mma_commit(&bar);
+          n += 8;
+          if ((n & 63) == 0) {  // keep the queue bounded: wait for every 8th batch
+            tc::mbar_wait(&bar, uint32_t((n / 8 - 1) & 1));
+          } else {
+            tc::mbar_wait(&bar, uint32_t((n / 8 - 1) & 1));
+          }
+        }
+        out[2] = n;
+      }
+      __syncwarp();
+    } else {
+      float a[16], b[16], c[16];
+      float acc = 0.f;
+      const long long e0 = clock64();
+      for (int r = 0; r < reps; ++r) {
+        if (var & 1) {
+          tc::tmem_ld16(lane_base + 0, a);
+          tc::tmem_ld16(lane_base + 32, b);
+          tc::tmem_ld16(lane_base + 64, c);
+          tc::tmem_ld_wait();
+        } else {
+          tc::tmem_ld16(lane_base + 0, a);
+          tc::tmem_ld_wait();
+          tc::tmem_ld16(lane_base + 32, b);
+          tc::tmem_ld_wait();
+          tc::tmem_ld16(lane_base + 64, c);
+          tc::tmem_ld_wait();
+        }
+        acc += a[0] + b[1] + c[2];
+      }
+      const long long e1 = clock64();
+      if (acc == 123.456f) out[63] = 1;
+      asm volatile("bar.sync 3, 224;\n" ::: "memory");  // warps 1-7
+      if (tid == 32) {
+        out[1] = e1 - e0;
+        stop13 = 1;
+      }
+    }
+    __syncthreads();
+    t0 = 0;
+    t1 = 0;
   } else if (mode == 4) {  // one conv-on-one-tile round trip: st -> sync -> MMA(s) -> commit -> wait -> ld
     const uint32_t idesc = tc::make_idesc(128, N, 0);
     const uint64_t ad = tc::make_desc(tc::smem_u32(smem), 128u * 16u, 128u);
@@ -281,7 +452,7 @@ __global__ void __launch_bounds__(256) tc_ubench_kernel(int mode, int N, int rep
     for (int r = 0; r < reps; ++r) __syncthreads();
     t1 = clock64();
   }
-  if (tid == 0 && !(mode >= 7 && mode <= 9)) out[1] = t1 - t0;
+  if (tid == 0 && !(mode >= 7 && mode <= 13)) out[1] = t1 - t0;
   tc::fence_before_sync();
   __syncthreads();
   if (warp == 0) tc::tmem_dealloc<512>(tmem);
@@ -292,8 +463,12 @@ double run_ubench(int mode, int N, int reps, int warps) {
   cudaMalloc(&d, 64 * sizeof(long long));
   cudaMemset(d, 0, 64 * sizeof(long long));
   cudaFuncSetAttribute(tc_ubench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-  tc_ubench_kernel<<<1, 256, 64 * 1024>>>(mode, N, reps, warps, d);
+  uint8_t* gsrc = nullptr;
+  cudaMalloc(&gsrc, 64 * 1024);
+  cudaMemset(gsrc, 0, 64 * 1024);
+  tc_ubench_kernel<<<1, 256, 64 * 1024>>>(mode, N, reps, warps, d, gsrc);
   cudaError_t e = cudaDeviceSynchronize();
+  cudaFree(gsrc);
   long long h = -1;
   if (e == cudaSuccess) cudaMemcpy(&h, d + 1, sizeof h, cudaMemcpyDeviceToHost);
   else {
@@ -342,7 +517,22 @@ extern "C" int32_t m3_selftest(int32_t which, double* result) {
     case 130: *result = m3::run_ubench(4, 32, 64, 0); break;   // st/sync/6 MMA/commit/wait/ld round trip
     case 131: *result = m3::run_ubench(4, 128, 64, 0); break;
     case 140: *result = m3::run_ubench(5, 0, 256, 0); break;   // __syncthreads
-    default: return M3_ERR_INVALID;
+    default:
+      // 200 + 100 * {0: N=32, 1: N=64, 2: N=128} + variant mask (mode 10): MMA stream as the conv kernels issue it
+      if (which >= 700 && which < 800) {  // 700 + variant: TMEM reads of 7 warps, sequential / batched, without / with an N=32 MMA stream
+        *result = m3::run_ubench(13, 32, 256, (which - 700) & 3);
+        return M3_OK;
+      }
+      if (which >= 500 && which < 700) {  // 500 + period: N=64, commit every `period` MMAs; 600 + period: + wait/fence per stage
+        *result = m3::run_ubench(which < 600 ? 11 : 12, 64, 480, (which - 500) % 100);
+        return M3_OK;
+      }
+      if (which >= 200 && which < 500) {
+        const int n = which < 300 ? 32 : which < 400 ? 64 : 128;
+        *result = m3::run_ubench(10, n, 512, (which - 200) % 100);
+        return M3_OK;
+      }
+      return M3_ERR_INVALID;
   }
   return M3_OK;
 }

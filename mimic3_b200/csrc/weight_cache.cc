@@ -19,7 +19,7 @@ namespace {
 // ---- tripwires: a field added to one of these structs must also be added to its io() below (and
 // kCacheLayoutVersion bumped); the sizes are those of the one platform this library is built for (x86-64 Linux).
 static_assert(sizeof(TcConvW) == 40 && sizeof(RowTcW) == 24 && sizeof(Lin) == 96, "update io(Lin) + layout version");
-static_assert(sizeof(FlowTcW) == 56 && sizeof(MrfStageW) == 104 && sizeof(DecLastW) == 88, "update io() + version");
+static_assert(sizeof(FlowTcW) == 80 && sizeof(MrfStageW) == 104 && sizeof(DecLastW) == 88, "update io() + version");
 static_assert(sizeof(UpW) == 80 && sizeof(DDSW) == 432 && sizeof(EncLayerW) == 432, "update io() + layout version");
 
 struct Writer {
@@ -180,7 +180,9 @@ void io(Ar& a, FlowTcW& f) {
   a.pod(f.ok); a.pod(f.woff);
   a.ptr(f.in_bias); a.ptr(f.cum_bias); a.ptr(f.skip_bias); a.ptr(f.post_bias);
   a.pod(f.x0_coff); a.pod(f.x1_coff);
+  a.pod(f.ok2); a.pod(f.woff2); a.ptr(f.m_bias);
   check_woff(a, f.woff);
+  check_woff(a, f.woff2);
 }
 template <typename Ar>
 void io(Ar& a, CouplingW& c) {

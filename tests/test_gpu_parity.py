@@ -530,3 +530,39 @@ def test_benchmarked_config2_parity_32x100_speaker0(sessions, oracles):
     for scales, seed in (((0.0, 1.0, 0.0), 0), ((0.667, 1.0, 0.8), 77)):
         worst, r = _compare_rows(sess, orc, ids, lens, sid, scales, seed, rows, f"cfg2 {scales}")
         print(f"cfg2 {scales}: {len(rows)} rows, worst RMS {worst:.3e}")
+
+
+def test_flow_second_generation_kernel_matches_first_and_unfused(sessions, oracles, monkeypatch):
+    """flow2_tc_kernel (kernels_tc_flow2.cu: post(skip) folded into pre-multiplied skip weights, N = 96 / 192 MMAs) against
+    the first fused kernel (M3B200_FLOW_V1=1), the per-conv kernels (M3B200_UNFUSED_FLOW=1) and the oracle, on a ragged
+    batch with one-window, many-window and one-frame-tail utterances, noise on (per-utterance conditioning in play)."""
+    rng = np.random.default_rng(2025)
+    sess, orc = sessions("low_ms"), oracles("low_ms")
+    lens_list = [1, 2, 27, 28, 80, 55, 3, 64] + [int(x) for x in rng.integers(4, 90, size=12)]
+    ids, lens = _batch(rng, 50, lens_list)
+    sid = rng.integers(0, 109, size=len(lens_list))
+    for scales, seed in (((0.0, 1.0, 0.0), 0), ((0.667, 1.0, 0.8), 7)):
+        new = sess.infer(ids, lens, scales, sid, seed=seed, keep_float=True, debug_tensors=("z_p", "z"))
+        monkeypatch.setenv("M3B200_FLOW_V1", "1")
+        v1 = sess.infer(ids, lens, scales, sid, seed=seed, keep_float=True, debug_tensors=("z_p", "z"))
+        monkeypatch.delenv("M3B200_FLOW_V1")
+        monkeypatch.setenv("M3B200_UNFUSED_FLOW", "1")
+        unf = sess.infer(ids, lens, scales, sid, seed=seed, keep_float=True, debug_tensors=("z_p", "z"))
+        monkeypatch.delenv("M3B200_UNFUSED_FLOW")
+        np.testing.assert_array_equal(new.frames, v1.frames)
+        np.testing.assert_array_equal(new.tensors["z_p"], v1.tensors["z_p"])
+        zn, z1, zu = new.tensors["z"], v1.tensors["z"], unf.tensors["z"]
+        ref = float(np.sqrt(np.mean(zu ** 2)))
+        for other, name in ((z1, "first fused kernel"), (zu, "unfused")):
+            rel = float(np.sqrt(np.mean((zn - other) ** 2))) / ref
+            print(f"scales {scales}: flow2 vs {name}: relative RMS {rel:.2e}")
+            assert rel < 3e-3, (name, rel)
+        for b in range(len(lens_list)):
+            a, c = new.utterance_audio(b), v1.utterance_audio(b)
+            # two independent 16-bit operand roundings of the flow (each within 5e-4 of the fp32 oracle at the waveform)
+            assert float(np.sqrt(np.mean((a - c) ** 2))) < 6e-4, b
+    for b in (0, 2, 4, 9):
+        audio = orc.infer(ids[b, :lens[b]], (0.0, 1.0, 0.0), sid=int(sid[b]))
+        got = sess.infer(ids[b:b + 1, :lens[b]], lens[b:b + 1], (0.0, 1.0, 0.0), sid[b:b + 1], keep_float=True).utterance_audio(0)
+        rms = float(np.sqrt(np.mean((got - audio) ** 2)))
+        assert rms <= RMS_TOL, (b, rms)

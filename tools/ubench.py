@@ -15,3 +15,25 @@ for k, n in names.items():
     v = ctypes.c_double()
     rc = lib.m3_selftest(k, ctypes.byref(v))
     print(f"{k}: {n:40s} rc={rc} cycles/rep = {v.value:.1f}")
+
+print("\nMMA stream as the conv kernels issue it (elect-issued, 4 accumulators, 512 MMAs); variant bits: 1 A start +16 B, "
+      "2 odd pitch (133 rows), 4 four A start rows, 8 four B blocks, 16 LSU traffic (4 warps STS/LDS.128), "
+      "32 8 KB bulk copies into smem, 64 A start +64 B")
+for n, base in ((32, 200), (64, 300), (128, 400)):
+    for var in (0, 1, 64, 2, 3, 4, 6, 14, 16, 32, 48, 15 + 16, 15 + 32, 15 + 48):
+        v = ctypes.c_double()
+        rc = lib.m3_selftest(base + var, ctypes.byref(v))
+        print(f"N={n:3d} variant {var:2d} ({var:06b}): rc={rc} cycles/MMA = {v.value:.1f}")
+
+print("\nN=64 MMA stream with a tcgen05.commit every P MMAs (5xx), plus a completed-mbarrier wait + fence per stage (6xx)")
+for base in (500, 600):
+    for period in (1, 2, 4, 6, 12, 24, 60):
+        v = ctypes.c_double()
+        rc = lib.m3_selftest(base + period, ctypes.byref(v))
+        print(f"{base + period}: period {period:2d}: rc={rc} cycles/MMA = {v.value:.1f}")
+
+print("\n7 warps x (3 tcgen05.ld x16 per round): 700 wait after each load, 701 one wait per round, 702/703 the same under an N=32 MMA stream")
+for k in (700, 701, 702, 703):
+    v = ctypes.c_double()
+    rc = lib.m3_selftest(k, ctypes.byref(v))
+    print(f"{k}: rc={rc} cycles/round = {v.value:.1f}")
