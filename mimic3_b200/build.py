@@ -23,8 +23,10 @@ OBJ = ROOT / "build" / "obj"
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function",
           "-I", str(ROOT / "include"), "-I", str(CSRC)]
-if os.environ.get("M3B200_KERNEL_PROFILE"):  # per-role cycle counters in the persistent kernels (debug builds only)
-    COMMON.append("-DM3B200_KERNEL_PROFILE")
+if os.environ.get("M3B200_KERNEL_PROFILE"):  # per-role cycle counters in the persistent kernels (debug builds only):
+    COMMON.append("-DM3B200_KERNEL_PROFILE")   # a separate library (select it with M3B200_LIBRARY) and object directory
+    OUT = PKG / "libm3b200_prof.so"
+    OBJ = ROOT / "build" / "obj_prof"
 
 
 def nvcc() -> str:

@@ -26,6 +26,13 @@
 
 namespace m3 {
 
+// per-role cycle counters (M3B200_MRF_PROFILE=1) exist only in builds made with M3B200_KERNEL_PROFILE=1 (see kernels_tc_mrf2.cu)
+#ifdef M3B200_KERNEL_PROFILE
+#define M3_PROF3(p) ((p).prof != nullptr)
+#else
+#define M3_PROF3(p) false
+#endif
+
 namespace {
 constexpr int bC = 128, bNT = 2, bR = bNT * 128, bCH = bC / 8, bKS = bC / 16;
 constexpr int bSegTable = 1024;
@@ -115,6 +122,16 @@ __global__ void __launch_bounds__((NEW + 3) * 32, 1) mrf_ws128_kernel(MrfParams 
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem = tmem_slot;
+  const bool prof = M3_PROF3(p);
+  auto timed_wait = [&](uint64_t* bar, uint32_t parity, long long& acc) {
+    if (prof && !tc::mbar_test(bar, parity)) {
+      const long long t = clock64();
+      tc::mbar_wait(bar, parity);
+      acc += clock64() - t;
+    } else {
+      tc::mbar_wait(bar, parity);
+    }
+  };
 
   if (warp == kLoader) {
     // =================================== weight loader ============================================
@@ -149,6 +166,8 @@ __global__ void __launch_bounds__((NEW + 3) * 32, 1) mrf_ws128_kernel(MrfParams 
       const uint32_t b_hi = uint32_t(b_tmpl >> 32), b_lo0 = uint32_t(b_tmpl);
       const int my_tile = warp - kIssuer;
       uint32_t slot = 0, fparity = 0u;
+      long long c_full = 0, c_x = 0, c_t = 0, c_y = 0;
+      const long long c_start = prof ? clock64() : 0;
       // one conv = k taps x 2 half-taps x 4 K-steps on this issuer's tile, all accumulating (the accumulator was
       // initialised by the epilogue warps)
       auto conv = [&](uint32_t abase, int rows_in, int halo, int k, int dil, uint32_t dcol) {
@@ -160,7 +179,7 @@ __global__ void __launch_bounds__((NEW + 3) * 32, 1) mrf_ws128_kernel(MrfParams 
         for (int t = 0; t < k; ++t, at += uint32_t(dil)) {
 #pragma unroll
           for (int hf = 0; hf < 2; ++hf) {
-            tc::mbar_wait(&bars[BFULL + slot], fparity);
+            timed_wait(&bars[BFULL + slot], fparity, c_full);
             tc::fence_after_sync();  // (measured free: r02l A/B with and without it)
             const uint32_t bt = b_lo0 + slot * (bSlotBytes >> 4);
 #pragma unroll
@@ -181,21 +200,30 @@ __global__ void __launch_bounds__((NEW + 3) * 32, 1) mrf_ws128_kernel(MrfParams 
       for (int idx = first; idx < total; idx = next_item(idx), ++it) {
         const uint32_t par = uint32_t(it) & 1u;
         const int win = idx % p.max_win;
-        tc::mbar_wait(&bars[BXT_READY], par);
+        timed_wait(&bars[BXT_READY], par, c_x);
         tc::fence_after_sync();
         for (int pos = 0; pos < 3; ++pos) {
           const int j = bchain_at(win, pos);
           if (pos > 0) {
-            tc::mbar_wait(&bars[BT_READY + pos - 1], par);
+            timed_wait(&bars[BT_READY + pos - 1], par, c_t);
             tc::fence_after_sync();
           }
           conv(tc::smem_u32(bufX), g.rows_x, p.HX, p.k[j], p.dil[j][0], bT0);
           tc::mma_commit(&bars[BC1_DONE + pos]);
-          tc::mbar_wait(&bars[BY_READY + pos], par);
+          timed_wait(&bars[BY_READY + pos], par, c_y);
           tc::fence_after_sync();
           conv(tc::smem_u32(bufY), g.rows_y, p.HY, p.k[j], p.dil[j][1], bS0);
         }
         tc::mma_commit(&bars[BC2_DONE]);
+      }
+      if (prof && my_tile == 0) {
+        unsigned long long* q = reinterpret_cast<unsigned long long*>(p.prof);
+        atomicAdd(q + 0, (unsigned long long)(clock64() - c_start));
+        atomicAdd(q + 1, (unsigned long long)c_full);
+        atomicAdd(q + 2, (unsigned long long)c_x);
+        atomicAdd(q + 3, (unsigned long long)c_t);
+        atomicAdd(q + 4, (unsigned long long)c_y);
+        atomicAdd(q + 5, (unsigned long long)it);
       }
     }
     __syncwarp();
@@ -291,6 +319,8 @@ __global__ void __launch_bounds__((NEW + 3) * 32, 1) mrf_ws128_kernel(MrfParams 
       }
     };
 
+    long long e_c1 = 0, e_c2 = 0;
+    const long long e_start = prof ? clock64() : 0;
     if (first < total) {
       init_T(first, bchain_at(first % p.max_win, 0), true);
       arrive(BXT_READY);
@@ -309,7 +339,7 @@ __global__ void __launch_bounds__((NEW + 3) * 32, 1) mrf_ws128_kernel(MrfParams 
 #pragma unroll 1
       for (int pos = 0; pos < 3; ++pos) {
         // ---- conv1 of the chain is complete: S += x1, Y <- lrelu(x1) ----
-        tc::mbar_wait(&bars[BC1_DONE + pos], par);
+        timed_wait(&bars[BC1_DONE + pos], par, e_c1);
         tc::fence_after_sync();
 #pragma unroll
         for (int m = 0; m < bNT; ++m) {
@@ -347,7 +377,7 @@ __global__ void __launch_bounds__((NEW + 3) * 32, 1) mrf_ws128_kernel(MrfParams 
         arrive(BXT_READY);
       }
       // ---- out = (S + late bias) / nk ----
-      tc::mbar_wait(&bars[BC2_DONE], par);
+      timed_wait(&bars[BC2_DONE], par, e_c2);
       tc::fence_after_sync();
       {
         const long long base = (long long)p.seg_off[seg] * p.scale;
@@ -378,6 +408,12 @@ __global__ void __launch_bounds__((NEW + 3) * 32, 1) mrf_ws128_kernel(MrfParams 
         }
       }
       idx = nxt;
+    }
+    if (prof && tid == 0) {
+      unsigned long long* q = reinterpret_cast<unsigned long long*>(p.prof);
+      atomicAdd(q + 8, (unsigned long long)(clock64() - e_start));
+      atomicAdd(q + 9, (unsigned long long)e_c1);
+      atomicAdd(q + 10, (unsigned long long)e_c2);
     }
   }
   tc::fence_before_sync();
@@ -426,6 +462,13 @@ void launch_mrf_ws128(const MrfParams& p_in, int fmt, int n_seg, int max_len, cu
   static const int new_warps = [] { const char* e = getenv("M3B200_MRF128_WARPS"); return e ? atoi(e) : 16; }();
   const long long items = (long long)n_seg * p.max_win;
   const int grid = int(items < n_sm ? items : n_sm);
+  static const bool want_prof = getenv("M3B200_MRF_PROFILE") != nullptr;
+  static long long* d_prof = nullptr;
+  if (want_prof) {
+    if (!d_prof) cudaMalloc(&d_prof, 16 * sizeof(long long));
+    cudaMemsetAsync(d_prof, 0, 16 * sizeof(long long), st);
+    p.prof = d_prof;
+  }
 #define M3_WS128(F, W)                                                                        \
   {                                                                                           \
     ensure_max_dynamic_smem(reinterpret_cast<const void*>(mrf_ws128_kernel<F, W>));           \
@@ -438,6 +481,16 @@ void launch_mrf_ws128(const MrfParams& p_in, int fmt, int n_seg, int max_len, cu
   }
 #undef M3_WS128
   post_launch("mrf_ws128_kernel", st);
+  if (want_prof) {  // debug only
+    long long h[16];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, d_prof, sizeof h, cudaMemcpyDeviceToHost);
+    const double w = h[5] > 0 ? double(h[5]) : 1.0;
+    fprintf(stderr,
+            "[mrf_ws128 profile] windows %lld grid %d | issuer cycles/window: total %.0f wait_full %.0f wait_xt %.0f wait_t %.0f wait_y %.0f | "
+            "epilogue warp0: total %.0f wait_c1 %.0f wait_c2 %.0f\n",
+            h[5], grid, h[0] / w, h[1] / w, h[2] / w, h[3] / w, h[4] / w, h[8] / w, h[9] / w, h[10] / w);
+  }
 }
 
 }  // namespace m3
