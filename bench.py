@@ -334,6 +334,9 @@ def main():
                     help="weak: --batch utterances PER GPU (default); strong: --batch utterances sharded over all GPUs")
     ap.add_argument("--profile-only", action="store_true", help="skip stage/e2e/cpu passes (ncu runs)")
     ap.add_argument("--e2e-depth", type=int, default=2, help="slots of the PCM collector (1 = no overlap of gather/D2H with compute)")
+    ap.add_argument("--gather", choices=("host", "nccl"), default="host",
+                    help="N>1 end-to-end PCM path: 'host' = every rank copies its PCM over its own PCIe link into one shared pinned "
+                         "host segment that rank 0 reads (no payload collective); 'nccl' = send/recv to rank 0's GPU, one D2H there")
     args = ap.parse_args()
     if not args.batch:
         args.batch = DEFAULT_BATCH[args.workload]
@@ -405,7 +408,7 @@ def main():
     # -- end to end: host ids in, int16 PCM back on the host ---------------------------------------------------
     scat = coll = None
     if distributed and not args.profile_only:
-        from mimic3_b200.shard import IdScatter, PcmCollector, make_groups
+        from mimic3_b200.shard import HostPcmCollector, IdScatter, PcmCollector, make_groups
         gather_pg, meta_pg = make_groups(dev)
         max_rows = max(j["ids"].shape[0] for j in jobs)
         max_t = max(j["T"] for j in jobs)
@@ -413,7 +416,10 @@ def main():
         scat = IdScatter(max_rows, max_t, dev, payload_group=None, meta_group=meta_pg)
         # capacity: generous bound per rank (ids x 12 frames/id x hop); the synthetic voices give 4-5 frames per id
         cap = per * max_t * 12 * 256
-        coll = PcmCollector(cap, per, dev, payload_group=gather_pg, meta_group=meta_pg, depth=max(1, args.e2e_depth))
+        if args.gather == "host":
+            coll = HostPcmCollector(cap, per, dev, meta_group=meta_pg, depth=max(1, args.e2e_depth))
+        else:
+            coll = PcmCollector(cap, per, dev, payload_group=gather_pg, meta_group=meta_pg, depth=max(1, args.e2e_depth))
     tickets = deque()
     trace = {"scatter": 0.0, "infer": 0.0, "submit": 0.0, "collect": 0.0, "n": 0} if os.environ.get("M3B200_BENCH_TRACE") else None
 
@@ -423,7 +429,8 @@ def main():
             return 0
         pcm, frames = got
         n = int(sum(int(np.sum(f)) for f in frames)) * 256
-        assert pcm.shape[0] == n, (pcm.shape, n)
+        have = sum(a.shape[0] for a in pcm) if isinstance(pcm, list) else pcm.shape[0]
+        assert have == n, (have, n)
         return n
 
     def step_e2e(seed):
@@ -577,8 +584,12 @@ def main():
                        "l2": "no flush: per-step activations (GBs) exceed the 126 MB L2 many times over",
                        "timing": "wall clock between barrier+synchronize pairs (>= CUDA-event time), max over ranks",
                        "device_event_ms_per_step": dev_max / args.steps * 1e3,
-                       "e2e_pipeline": (f"N>1: id scatter (pinned H2D + NCCL) and PCM gather (NCCL send/recv + one D2H to pinned memory on "
-                                        f"rank 0) every step, {max(1, args.e2e_depth)} slots: step k's gather/D2H overlap step k+1's compute")
+                       "e2e_pipeline": ((f"N>1: id scatter (pinned H2D + NCCL) every step; PCM: every rank copies its own int16 PCM over its own "
+                                         f"PCIe link into its slice of ONE shared pinned host segment that rank 0 reads (no payload collective), "
+                                         f"{max(1, args.e2e_depth)} slots: step k's copies overlap step k+1's compute"
+                                         if args.gather == "host" else
+                                         f"N>1: id scatter (pinned H2D + NCCL) and PCM gather (NCCL send/recv + one D2H to pinned memory on "
+                                         f"rank 0) every step, {max(1, args.e2e_depth)} slots: step k's gather/D2H overlap step k+1's compute"))
                                        if distributed else "N=1: m3_infer with host ids, PCM copied to pinned host memory inside the call"},
             "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
             "roofline": {"kernel": k_name, "bound": "tensor", "achieved": achieved_tf,

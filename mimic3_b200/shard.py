@@ -19,6 +19,13 @@ compute, all of it in per-step allocations, ``.item()`` syncs, a padded ``dist.g
   Slots are double-buffered: step k's gather + D2H run while step k+1 computes (372 MB through one
   PCIe Gen5 link is ~7 ms, under the 16.6 ms of compute it hides behind).
 
+* :class:`HostPcmCollector` -- the gather WITHOUT a payload collective: every rank copies its own PCM
+  device -> host over its OWN PCIe link into its slice of one POSIX shared-memory segment (pinned with
+  ``cudaHostRegister``) that rank 0 reads.  With the NCCL gather all of the step's PCM (46 MB per GPU, 373 MB at
+  8 GPUs) funnels through rank 0's GPU and its single PCIe link while that GPU is also computing its own shard:
+  measured 0.82 of linear end to end at 4 GPUs (r02p).  Per-rank copies are 1 ms each, in parallel, hidden under
+  the next step.  Same interface as :class:`PcmCollector`; ``collect`` returns one int16 view per rank.
+
 The same classes run over a single gloo group on CPU tensors (``tests/test_sharding_gloo.py``).
 """
 from __future__ import annotations
@@ -234,6 +241,127 @@ class PcmCollector:
                 self.pending[i] = None
         if self.cuda:
             self.torch.cuda.synchronize(self.device)
+
+
+class HostPcmCollector:
+    """PCM of every rank in ONE shared pinned host segment that rank 0 reads; no payload collective (module docstring).
+
+    Every rank: ``buf = c.send_buffer()`` (persistent device buffer the engine writes its PCM into),
+    ``t = c.submit(n_samples, frames_per_utterance)`` (async D2H of this rank's samples into its slice + a host-side
+    gather of the counts), and -- every rank, same order -- ``c.collect(t)``: waits for the own copy, then a host
+    barrier; rank 0 gets ``([int16 view per rank], [frame counts per rank])``, valid until the slot is reused.
+    """
+
+    def __init__(self, capacity_samples: int, max_rows_per_rank: int, device, meta_group=None, depth: int = 2):
+        import torch
+        import torch.distributed as dist
+        from multiprocessing import shared_memory
+        self.dist, self.torch = dist, torch
+        self.mg = meta_group
+        self.world, self.rank = dist.get_world_size(meta_group), dist.get_rank(meta_group)
+        self.device = torch.device(device)
+        self.cuda = self.device.type == "cuda"
+        self.depth, self.k = depth, 0
+        self.per = max_rows_per_rank
+        self.cap = int(capacity_samples)
+        nbytes = 2 * self.cap * self.world * depth
+        name = [None]
+        if self.rank == 0:
+            self.shm = shared_memory.SharedMemory(create=True, size=nbytes)
+            name[0] = self.shm.name
+        dist.broadcast_object_list(name, src=0, group=meta_group)
+        if self.rank != 0:
+            self.shm = shared_memory.SharedMemory(name=name[0])
+        # layout [rank][slot][cap]: a rank's slices are one contiguous region (one cudaHostRegister)
+        self.all = torch.from_numpy(np.ndarray((self.world, depth, self.cap), dtype=np.int16, buffer=self.shm.buf))
+        self.mine = self.all[self.rank]
+        self._registered = None
+        if self.cuda:
+            ptr, size = self.mine.data_ptr(), self.mine.numel() * 2
+            rc = torch.cuda.cudart().cudaHostRegister(ptr, size, 0)
+            if int(rc) != 0:
+                raise RuntimeError(f"cudaHostRegister of the shared PCM segment failed ({rc})")
+            self._registered = ptr
+            self.copy_stream = torch.cuda.Stream(self.device)
+            self.events = [torch.cuda.Event() for _ in range(depth)]
+        self.src = [torch.zeros(self.cap, dtype=torch.int16, device=self.device) for _ in range(depth)]
+        self.pending: List[Optional[PcmTicket]] = [None] * depth
+        self.meta_mine = torch.zeros(2 + self.per, dtype=torch.int64)
+        self.meta_all = [torch.zeros(2 + self.per, dtype=torch.int64) for _ in range(self.world)] if self.rank == 0 else None
+        dist.barrier(group=meta_group)
+
+    def _slot(self) -> int:
+        return self.k % self.depth
+
+    def send_buffer(self):
+        s = self._slot()
+        t = self.pending[s]
+        if t is not None:          # the slot's previous D2H must have left the device buffer
+            if t.event is not None:
+                t.event.synchronize()
+            self.pending[s] = None
+        return self.src[s]
+
+    def submit(self, n_samples: int, frames) -> PcmTicket:
+        torch, dist = self.torch, self.dist
+        s = self._slot()
+        self.k += 1
+        if n_samples > self.cap:
+            raise ValueError(f"{n_samples} samples exceed the collector capacity {self.cap}")
+        frames = np.asarray(frames, dtype=np.int64)
+        t = PcmTicket()
+        t.slot, t.event, t.works, t.total = s, None, None, int(n_samples)
+        if n_samples:
+            if self.cuda:
+                with torch.cuda.stream(self.copy_stream):       # the engine call has completed: src[s] is final
+                    self.mine[s][:n_samples].copy_(self.src[s][:n_samples], non_blocking=True)
+                    t.event = self.events[s]
+                    t.event.record(self.copy_stream)
+            else:
+                self.mine[s][:n_samples].copy_(self.src[s][:n_samples])
+        self.meta_mine.zero_()
+        self.meta_mine[0], self.meta_mine[1] = int(n_samples), len(frames)
+        self.meta_mine[2: 2 + len(frames)] = torch.from_numpy(frames)
+        dist.gather(self.meta_mine, self.meta_all, dst=0, group=self.mg)   # host side: counts + frames per utterance
+        if self.rank == 0:
+            t.counts = [int(m[0]) for m in self.meta_all]
+            t.frames = [m[2: 2 + int(m[1])].numpy().copy() for m in self.meta_all]
+            t.total = sum(t.counts)
+        else:
+            t.counts = t.frames = None
+        self.pending[s] = t
+        return t
+
+    def collect(self, t: PcmTicket):
+        """EVERY rank calls this, in submit order.  Rank 0: ([int16 numpy view of rank r's samples], frames)."""
+        if t.event is not None:
+            t.event.synchronize()
+        self.dist.barrier(group=self.mg)                          # every rank's copy has landed in the segment
+        if self.rank != 0:
+            return None
+        return [self.all[r][t.slot][: t.counts[r]].numpy() for r in range(self.world)], t.frames
+
+    def drain(self):
+        for i, t in enumerate(self.pending):
+            if t is not None and t.event is not None:
+                t.event.synchronize()
+            self.pending[i] = None
+        if self.cuda:
+            self.torch.cuda.synchronize(self.device)
+
+    def close(self):
+        self.drain()
+        if self._registered is not None:
+            self.torch.cuda.cudart().cudaHostUnregister(self._registered)
+            self._registered = None
+        self.all = self.mine = None
+        try:
+            self.dist.barrier(group=self.mg)
+            self.shm.close()
+            if self.rank == 0:
+                self.shm.unlink()
+        except Exception:  # pragma: no cover
+            pass
 
 
 def make_groups(device):

@@ -26,19 +26,22 @@ def test_shard_bounds_cover_and_balance():
     assert max(loads) <= 1800 + 41  # longest-first greedy: no rank far above the biggest item
 
 
-def _worker(rank, world, port, tmp):
+def _worker(rank, world, port, tmp, transport="nccl"):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     sys.path.insert(0, str(ROOT))
     import torch
     import torch.distributed as dist
-    from mimic3_b200.shard import IdScatter, PcmCollector, make_groups, shard_bounds
+    from mimic3_b200.shard import HostPcmCollector, IdScatter, PcmCollector, make_groups, shard_bounds
     dist.init_process_group("gloo", rank=rank, world_size=world)
     pg, mg = make_groups("cpu")
     B, T = 7, 11
     scatter = IdScatter(max_rows=9, max_t=16, device="cpu", payload_group=pg, meta_group=mg)
     per = (9 + world - 1) // world
-    collector = PcmCollector(capacity_samples=per * 16 * 4, max_rows_per_rank=per, device="cpu", payload_group=pg,
-                             meta_group=mg, depth=2)
+    if transport == "host":   # every rank writes its own slice of one shared-memory segment; no payload collective
+        collector = HostPcmCollector(capacity_samples=per * 16 * 4, max_rows_per_rank=per, device="cpu", meta_group=mg, depth=2)
+    else:
+        collector = PcmCollector(capacity_samples=per * 16 * 4, max_rows_per_rank=per, device="cpu", payload_group=pg,
+                                 meta_group=mg, depth=2)
     tickets, want = [], []
     for step in range(5):      # more steps than slots: buffers are reused, nothing is allocated per step
         rng = np.random.default_rng(step)
@@ -68,6 +71,8 @@ def _worker(rank, world, port, tmp):
     while tickets:
         _check(collector.collect(tickets.pop(0)), want.pop(0), rank, world)
     collector.drain()
+    if hasattr(collector, "close"):
+        collector.close()
     if rank == 0:
         Path(tmp, "ok").write_text("ok")
     dist.destroy_process_group()
@@ -79,6 +84,9 @@ def _check(out, want, rank, world):
         assert out is None
         return
     pcm, frames = out
+    if isinstance(pcm, list):     # HostPcmCollector: one view per rank, rank order == row order
+        assert len(pcm) == world and all(a.dtype == np.int16 for a in pcm)
+        pcm = np.concatenate(pcm)
     assert len(frames) == world
     flat = np.concatenate([np.asarray(f) for f in frames])
     assert np.array_equal(flat, lengths)                      # rank order == row order
@@ -101,4 +109,12 @@ def test_scatter_gather_world3_gloo(tmp_path):
     import torch.multiprocessing as mp
     port = 31500 + (os.getpid() % 2000)
     mp.spawn(_worker, args=(3, port, str(tmp_path)), nprocs=3, join=True)
+    assert (tmp_path / "ok").exists()
+
+
+def test_host_segment_collector_world3_gloo(tmp_path):
+    """HostPcmCollector: same steps, same checks, PCM through one POSIX shared-memory segment instead of send/recv."""
+    import torch.multiprocessing as mp
+    port = 33500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(3, port, str(tmp_path), "host"), nprocs=3, join=True)
     assert (tmp_path / "ok").exists()
