@@ -743,6 +743,7 @@ PackedVoice pack_voice(const HostVoice& hv) {
         }
         dl.blob_bytes = here();
         dl.fused_ok = dec_fused_supported(C, u.cin, u.k, u.u, ms.nk, ms.nd, ms.HX, dl.HYb, dl.blob_bytes);
+        dl.planes_ok = dl.fused_ok && dec_planes_supported(C, u.cin, u.k, u.u, ms.nk, ms.nd, ms.HX, dl.HYb, dl.blob_bytes);
       }
     }
   }
@@ -1492,7 +1493,9 @@ Result* run_inference(Voice& v, const int64_t* ids, const int64_t* lengths, int 
       fp.seg_len = d_frm_len;
       fp.HX = ms.HX;
       fp.H = ms.HX + hymax + 3;
-      launch_dec_fused(fp, dv.tc_fmt, batch, Fmax, st);
+      // M3B200_DEC_V2=1: second-generation kernel (sample-order windows); read per call so that one process can A/B them
+      if (dl.planes_ok && !getenv("M3B200_DEC_V2")) launch_dec_planes(fp, dv.tc_fmt, batch, Fmax, st);
+      else launch_dec_fused(fp, dv.tc_fmt, batch, Fmax, st);
       R.mark("dec_last");
       scale = out_scale;
       audio_done = true;

@@ -107,6 +107,7 @@ struct DecLastW {  // fused last generator stage (kernels_tc_dec.cu)
   unsigned long long up_woff = 0, post_woff = 0;
   // persistent kernel (kernels_tc_dec2.cu): one contiguous blob, byte offsets relative to blob_off
   bool fused_ok = false;
+  bool planes_ok = false;  // phase-major kernel (kernels_tc_dec3.cu) can run this stage
   unsigned long long blob_off = 0;  // element offset in slab16
   unsigned blob_bytes = 0, f_up = 0, f_post = 0, f_c1[3] = {}, f_c2[3] = {};
   int HYb[3] = {};

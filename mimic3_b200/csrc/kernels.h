@@ -202,10 +202,15 @@ struct DecFusedParams {
   const int* seg_len = nullptr;
   int H = 0, HX = 0, HYb[3] = {};  // HYb: halo rows of resblock j's second-conv operand buffer (>= 3 for j = 0: conv_post reuses it)
   int stride = 0, n_seg = 0, max_win = 0;  // filled by the launcher
+  int HL = 0;                              // dec_planes_kernel: left halo of a window (launcher; >= H, aligns windows to the upsampling phase)
   long long* prof = nullptr;               // M3B200_DEC_PROFILE=1: per-role cycle counters (debug)
 };
 bool dec_fused_supported(int C, int cin, int up_k, int up_u, int nk, int nd, int HX, const int* HYb, size_t w_bytes);
 void launch_dec_fused(const DecFusedParams& p, int fmt, int n_seg, int max_len, cudaStream_t st);
+// Third generation (kernels_tc_dec3.cu): same blob and parameters, the stage kept in phase-major planes (u = 4, cin = 64):
+// 512-sample windows, no transposition of the transposed-conv result, two issuer warps.
+bool dec_planes_supported(int C, int cin, int up_k, int up_u, int nk, int nd, int HX, const int* HYb, size_t w_bytes);
+void launch_dec_planes(const DecFusedParams& p, int fmt, int n_seg, int max_len, cudaStream_t st);
 
 // Fused coupling layer of the flow (kernels_tc_flow.cu).  Weights: one 16-bit stream in schedule order
 // (pre chunks | per layer: gate chunks x 5 taps, res chunks, skip chunks | post chunks), each stage

@@ -102,6 +102,11 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ float tmem_ld1(uint32_t taddr) {
+  uint32_t r;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];\n" : "=r"(r) : "r"(taddr) : "memory");
+  return __uint_as_float(r);
+}
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float* v) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};\n" ::"r"(taddr),
                "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),

@@ -216,7 +216,7 @@ void io(Ar& a, MrfStageW& m) {
 }
 template <typename Ar>
 void io(Ar& a, DecLastW& d) {
-  a.pod(d.ok); a.pod(d.up_woff); a.pod(d.post_woff); a.pod(d.fused_ok); a.pod(d.blob_off); a.pod(d.blob_bytes);
+  a.pod(d.ok); a.pod(d.up_woff); a.pod(d.post_woff); a.pod(d.fused_ok); a.pod(d.planes_ok); a.pod(d.blob_off); a.pod(d.blob_bytes);
   a.pod(d.f_up); a.pod(d.f_post);
   for (int i = 0; i < 3; ++i) { a.pod(d.f_c1[i]); a.pod(d.f_c2[i]); a.pod(d.HYb[i]); }
   check_woff(a, d.up_woff);

@@ -326,9 +326,9 @@ def test_text_side_tensor_core_split_keeps_durations(voices, built_library, monk
 
 
 def test_persistent_last_stage_matches_per_window_kernel_and_oracle(voices, built_library, oracles, monkeypatch):
-    """The persistent warp-specialised last-stage kernel (polyphase transposed conv, kernels_tc_dec2.cu)
-    against the per-window fused kernel, the unfused kernels and the oracle, on a ragged batch that mixes
-    one-window utterances, many-window utterances and more work items than SMs."""
+    """The persistent warp-specialised last-stage kernels (phase-major planes, kernels_tc_dec3.cu = default; sample-order
+    windows, kernels_tc_dec2.cu) against the per-window fused kernel, the unfused kernels and the oracle, on a ragged
+    batch that mixes one-window utterances, many-window utterances and more work items than SMs."""
     from mimic3_b200.engine import B200Session
     rng = np.random.default_rng(77)
     orc = oracles("low_ms")
@@ -339,6 +339,9 @@ def test_persistent_last_stage_matches_per_window_kernel_and_oracle(voices, buil
     sess = B200Session(str(voices("low_ms")))
     got = sess.infer(ids, lens, scales, sid, keep_float=True)
     again = sess.infer(ids, lens, scales, sid, keep_float=True)
+    monkeypatch.setenv("M3B200_DEC_V2", "1")
+    v2 = sess.infer(ids, lens, scales, sid, keep_float=True)
+    monkeypatch.delenv("M3B200_DEC_V2")
     monkeypatch.setenv("M3B200_DEC_V1", "1")
     v1 = sess.infer(ids, lens, scales, sid, keep_float=True)
     monkeypatch.delenv("M3B200_DEC_V1")
@@ -351,7 +354,7 @@ def test_persistent_last_stage_matches_per_window_kernel_and_oracle(voices, buil
     np.testing.assert_array_equal(got.frames, v1.frames)
     np.testing.assert_array_equal(got.audio, again.audio)   # deterministic: no order-dependent accumulation
     np.testing.assert_array_equal(got.peaks, again.peaks)
-    for other, name in ((v1, "per-window fused"), (unf, "unfused"), (mrf_v1, "per-window MRF")):
+    for other, name in ((v2, "sample-order persistent"), (v1, "per-window fused"), (unf, "unfused"), (mrf_v1, "per-window MRF")):
         for b in range(len(lens_list)):
             a, c = got.utterance_audio(b), other.utterance_audio(b)
             rms = float(np.sqrt(np.mean((a - c) ** 2)))
