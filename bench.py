@@ -557,10 +557,10 @@ def main():
         mrf_ms = stage_ms["mrf"] / args.steps
         traffic = traffic_src = None
         if dec_ms > 0:   # dominant kernel: the fused last generator stage (upsample + MRF + conv_post)
-            k_name = "dec_fused_kernel (ConvTranspose + MRF + conv_post, last generator stage)"
+            k_name = "dec_planes_kernel (ConvTranspose + MRF + conv_post, last generator stage; dec_fused_kernel with M3B200_DEC_V2=1)"
             k_flops = (fl["ups_stage"][-1] + fl["mrf_stage"][-1] + fl["post"]) * frames_ps
             k_ms = dec_ms
-            per_sample, traffic_src = measured_traffic("dec_fused_kernel")
+            per_sample, traffic_src = measured_traffic("dec_fused_kernel" if os.environ.get("M3B200_DEC_V2") else "dec_planes_kernel")
             if per_sample is not None:
                 traffic = per_sample * frames_ps * 256
         else:

@@ -742,8 +742,25 @@ PackedVoice pack_voice(const HostVoice& hv) {
           std::copy(B.h16.begin() + src, B.h16.begin() + src + n, B.h16.begin() + o);
         }
         dl.blob_bytes = here();
+        dl.f_postp = here();
+        {  // conv_post for the phase-major kernel (kernels.h: kDecPostPlanesBytes); the v2 kernel never loads past blob_bytes
+          const size_t o = B.h16.size();
+          B.h16.resize(o + kDecPostPlanesBytes / 2, 0);
+          int pair = 0;
+          for (int sh = -1; sh <= 1; ++sh)
+            for (int pi = 0; pi < 4; ++pi) {
+              if ((sh < 0 && pi == 0) || (sh > 0 && pi == 3)) continue;
+              for (int php = 0; php < 4; ++php) {
+                const int tap = 4 * sh + pi - php + 3;
+                if (tap < 0 || tap > 6) continue;
+                for (int ci = 0; ci < C; ++ci)
+                  B.h16[o + ((size_t(pair) * (C / 8) + ci / 8) * 16 + php) * 8 + (ci & 7)] = B.cvt16(pw.f32[size_t(ci) * 7 + tap]);
+              }
+              ++pair;
+            }
+        }
         dl.fused_ok = dec_fused_supported(C, u.cin, u.k, u.u, ms.nk, ms.nd, ms.HX, dl.HYb, dl.blob_bytes);
-        dl.planes_ok = dl.fused_ok && dec_planes_supported(C, u.cin, u.k, u.u, ms.nk, ms.nd, ms.HX, dl.HYb, dl.blob_bytes);
+        dl.planes_ok = dl.fused_ok && dec_planes_supported(C, u.cin, u.k, u.u, ms.nk, ms.nd, ms.HX, dl.HYb, dl.f_post + kDecPostPlanesBytes);
       }
     }
   }
@@ -1494,7 +1511,11 @@ Result* run_inference(Voice& v, const int64_t* ids, const int64_t* lengths, int 
       fp.HX = ms.HX;
       fp.H = ms.HX + hymax + 3;
       // M3B200_DEC_V2=1: second-generation kernel (sample-order windows); read per call so that one process can A/B them
-      if (dl.planes_ok && !getenv("M3B200_DEC_V2")) launch_dec_planes(fp, dv.tc_fmt, batch, Fmax, st);
+      if (dl.planes_ok && !getenv("M3B200_DEC_V2")) {
+        fp.w_bytes = dl.f_post + kDecPostPlanesBytes;  // shared-memory image: blob[0, f_post) | regrouped conv_post
+        fp.post_planes_src = dl.f_postp;
+        launch_dec_planes(fp, dv.tc_fmt, batch, Fmax, st);
+      }
       else launch_dec_fused(fp, dv.tc_fmt, batch, Fmax, st);
       R.mark("dec_last");
       scale = out_scale;

@@ -102,6 +102,8 @@ struct MrfStageW {  // tensor-core packing of one MRF stage (kernels_tc.cu)
   int H = 0, HX = 0, HY = 0, nk = 0, nd = 0;
 };
 
+constexpr unsigned kDecPostPlanesBytes = 10 * 4 * 16 * 8 * 2;  // regrouped conv_post of dec_planes_kernel (kernels.h)
+
 struct DecLastW {  // fused last generator stage (kernels_tc_dec.cu)
   bool ok = false;
   unsigned long long up_woff = 0, post_woff = 0;
@@ -110,6 +112,7 @@ struct DecLastW {  // fused last generator stage (kernels_tc_dec.cu)
   bool planes_ok = false;  // phase-major kernel (kernels_tc_dec3.cu) can run this stage
   unsigned long long blob_off = 0;  // element offset in slab16
   unsigned blob_bytes = 0, f_up = 0, f_post = 0, f_c1[3] = {}, f_c2[3] = {};
+  unsigned f_postp = 0;  // conv_post regrouped by (row shift, input plane) for the phase-major kernel; lies past blob_bytes
   int HYb[3] = {};
 };
 

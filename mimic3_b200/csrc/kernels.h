@@ -203,12 +203,16 @@ struct DecFusedParams {
   int H = 0, HX = 0, HYb[3] = {};  // HYb: halo rows of resblock j's second-conv operand buffer (>= 3 for j = 0: conv_post reuses it)
   int stride = 0, n_seg = 0, max_win = 0;  // filled by the launcher
   int HL = 0;                              // dec_planes_kernel: left halo of a window (launcher; >= H, aligns windows to the upsampling phase)
+  unsigned post_planes_src = 0;            // dec_planes_kernel: byte offset in wblob of conv_post regrouped per (row shift, input plane)
   long long* prof = nullptr;               // M3B200_DEC_PROFILE=1: per-role cycle counters (debug)
 };
 bool dec_fused_supported(int C, int cin, int up_k, int up_u, int nk, int nd, int HX, const int* HYb, size_t w_bytes);
 void launch_dec_fused(const DecFusedParams& p, int fmt, int n_seg, int max_len, cudaStream_t st);
 // Third generation (kernels_tc_dec3.cu): same blob and parameters, the stage kept in phase-major planes (u = 4, cin = 64):
-// 512-sample windows, no transposition of the transposed-conv result, two issuer warps.
+// 512-sample windows, no transposition of the transposed-conv result, two issuer warps.  conv_post (one output channel)
+// is regrouped: output column = output plane ph', one [C/8][16][8] block per (row shift sh, input plane pi) in the order
+// sh = -1: pi 1..3, sh = 0: pi 0..3, sh = +1: pi 0..2, block column ph' = w[tap 4 sh + pi - ph' + 3] -- 20 MMAs per window
+// instead of 56.  The kernel's shared-memory weight image is blob[0, post.woff) followed by those kDecPostPlanesBytes (engine.h).
 bool dec_planes_supported(int C, int cin, int up_k, int up_u, int nk, int nd, int HX, const int* HYb, size_t w_bytes);
 void launch_dec_planes(const DecFusedParams& p, int fmt, int n_seg, int max_len, cudaStream_t st);
 

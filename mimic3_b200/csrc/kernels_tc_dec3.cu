@@ -19,10 +19,15 @@
 //   * the next window's transposed conv (into T_0, free once chain 0's epilogue has read it) and its epilogue run
 //     BEFORE this window's final epilogue, so the tensor pipe goes straight from c2 of window w to c1 of window w+1
 //     while the epilogue warps reduce window w and conv_post(w) slots in between c1_1 and c1_2 of w+1;
-//   * two issuer warps (planes 0-1 / planes 2-3): 304 MMAs per window would make one issuing thread the limiter.
+//   * two issuer warps (planes 0-1 / planes 2-3): ~270 MMAs per window would make one issuing thread the limiter;
+//   * conv_post (ONE output channel) no longer runs as 7 taps x 4 planes of N=16 MMAs: its output COLUMN is the output plane
+//     ph', and the input side is grouped by (row shift sh, input plane pi) -- 10 groups x 2 k-steps = 20 MMAs per window
+//     instead of 56 (each costs its 4.6 KB operand fetch whatever it computes), and a thread reads the four samples
+//     4t..4t+3 of its row with one 4-column TMEM load.  The two issuers accumulate five groups each into their own
+//     16-column tile; the epilogue adds the two.
 // Window origins are chosen so that (w0 + up_pad) % 4 == 0: plane ph IS polyphase ph, no lane shift anywhere.
 // TMEM (512 columns): T_j = [128 j, 128 j + 128) conv1 accumulators of chain j, plane ph at +32 ph (T_0 doubles as the
-// transposed-conv result D of the NEXT window), S = [384, 512) all second convs (conv_post reuses [384, 448)).
+// transposed-conv result D of the NEXT window), S = [384, 512) all second convs (conv_post reuses [384, 416)).
 #include <cstdio>
 #include <cstdlib>
 #include <stdexcept>
@@ -77,6 +82,80 @@ __host__ __device__ inline Geo make_geo(const DecFusedParams& p) {
   return g;
 }
 __device__ __forceinline__ float lrelu(float v, float s) { return fmaxf(v, s * v); }
+
+// Tuning knobs (compile-time; tools/build_variant.sh builds A/B libraries):
+#ifndef DEC3_BATCH       // accumulator planes pulled out of TMEM per tcgen05.wait::ld (1, 2 or 4).  Measured (r02u, dec_last ms):
+#define DEC3_BATCH 1      // 1: 2.89, 2: 3.00, 4: 3.99 (spills) -- the 16 warps hide the load latency, registers are the scarcer resource
+#endif
+#ifndef DEC3_F32X2       // packed fp32 pair arithmetic (FADD2 / FMUL2) in the epilogues.  Measured (r02u): 1: 3.00, 0: 3.08
+#define DEC3_F32X2 1
+#endif
+#ifndef DEC3_H2          // fp16 operands only: leaky-relu and the running sum of x1_j on packed half pairs (HMUL2 / HMNMX2 / HADD2)
+#define DEC3_H2 1         // instead of fp32 + converts: ~60 -> ~38 instructions per plane row of a chain epilogue
+#endif
+#ifndef DEC3_KO           // timing knock-outs (results wrong, attribution only): 1 no MMAs, 2 epilogues without TMEM loads and
+#define DEC3_KO 0         // math (zeros stored), 3 epilogues with TMEM loads but no math
+#endif
+#ifndef DEC3_POLL_ALL    // 1: every lane of a waiting epilogue warp polls its mbarrier; 0: lane 0 polls + __syncwarp.  Measured (r02u):
+#define DEC3_POLL_ALL 1   // 1: 2.89, 0: 3.00 -- the single poller wakes its warp later than the hardware wakes 32 suspended lanes
+#endif
+
+// fp32 pairs in one 64-bit register: sm_100 executes add / mul on both halves in one instruction (FADD2 / FMUL2);
+// the epilogue warps are issue-bound (ncu r02s: ~1400 instructions per warp and window, 97 % busy), so halving the
+// fp32 adds of the residual / bias / running-sum path is time, not style.
+__device__ __forceinline__ unsigned long long pk64(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void un64(unsigned long long v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) {
+#if DEC3_F32X2
+  unsigned long long r;
+  asm("add.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+#else
+  float a0, a1, b0, b1;
+  un64(a, a0, a1);
+  un64(b, b0, b1);
+  return pk64(a0 + b0, a1 + b1);
+#endif
+}
+__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) {
+#if DEC3_F32X2
+  unsigned long long r;
+  asm("mul.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+#else
+  float a0, a1, b0, b1;
+  un64(a, a0, a1);
+  un64(b, b0, b1);
+  return pk64(a0 * b0, a1 * b1);
+#endif
+}
+// 16-bit operand pair of lrelu(v, slope) for an fp32 pair.  Half-pair variant (fp16 operands): round first, then
+// max(h, slope * h) on the pair -- identical for v >= 0; for v < 0 the result carries two more fp16 roundings of a value
+// that is 10x (100x) smaller than its positive-side neighbours' rounding errors, i.e. noise below the operand format's own.
+template <class E, int FMT>
+__device__ __forceinline__ uint32_t lrelu_op(unsigned long long v, unsigned long long slope2, float slope) {
+  if constexpr (DEC3_H2 && FMT == 0) {
+    float a, b;
+    un64(v, a, b);
+    return E::lrelu2(E::pack2(a, b), slope);
+  } else {
+    float a, b, c, d;
+    un64(v, a, b);
+    un64(mul2(v, slope2), c, d);
+    return E::pack2(fmaxf(a, c), fmaxf(b, d));
+  }
+}
+template <class E>
+__device__ __forceinline__ uint32_t lrelu_pack(unsigned long long v, unsigned long long slope2) {
+  float a, b, c, d;
+  un64(v, a, b);
+  un64(mul2(v, slope2), c, d);
+  return E::pack2(fmaxf(a, c), fmaxf(b, d));
+}
 }  // namespace
 
 template <int FMT>
@@ -149,7 +228,16 @@ __global__ void __maxnreg__(96) dec_planes_kernel(DecFusedParams p) {
 #else
   constexpr bool prof = false;
 #endif
-  auto timed_wait = [&](uint64_t* bar, uint32_t parity, long long& acc) {
+  auto warp_wait = [&](uint64_t* bar, uint32_t parity, long long& acc) {  // all lanes of a warp call it; lane 0 polls
+    if (prof && !tc::mbar_test(bar, parity)) {
+      const long long t = clock64();
+      DEC3_POLL_ALL ? tc::mbar_wait(bar, parity) : tc::mbar_wait_warp(bar, parity);
+      acc += clock64() - t;
+    } else {
+      DEC3_POLL_ALL ? tc::mbar_wait(bar, parity) : tc::mbar_wait_warp(bar, parity);
+    }
+  };
+  auto timed_wait = [&](uint64_t* bar, uint32_t parity, long long& acc) {  // single-thread wait (the elected issuers)
     if (prof && !tc::mbar_test(bar, parity)) {  // only waits that actually block are timed
       const long long t = clock64();
       tc::mbar_wait(bar, parity);
@@ -166,16 +254,18 @@ __global__ void __maxnreg__(96) dec_planes_kernel(DecFusedParams p) {
       if (warp == kLoader && tc::elect_one()) {
         tc::mbar_expect_tx(&bars[W_FULL], p.w_bytes);
         const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wblob);
-        for (uint32_t o = 0; o < p.w_bytes; o += 32768u) {
-          const uint32_t n = p.w_bytes - o < 32768u ? p.w_bytes - o : 32768u;
+        const uint32_t main_bytes = p.post.woff;  // blob[0, post.woff): up | c1 / c2 of the three chains
+        for (uint32_t o = 0; o < main_bytes; o += 32768u) {
+          const uint32_t n = main_bytes - o < 32768u ? main_bytes - o : 32768u;
           tc::bulk_g2s(wts + o, src + o, n, &bars[W_FULL]);
         }
+        tc::bulk_g2s(wts + main_bytes, src + p.post_planes_src, p.w_bytes - main_bytes, &bars[W_FULL]);  // regrouped conv_post
       }
       __syncwarp();
       const int items = g.rows_a * CHI;
       int it = 0;
       for (int idx = first; idx < total; idx = next_item(idx), ++it) {
-        if (it > 0) tc::mbar_wait(&bars[U_DONE], uint32_t(it - 1) & 1u);  // previous window's transposed conv has read bufA
+        if (it > 0) tc::mbar_wait_warp(&bars[U_DONE], uint32_t(it - 1) & 1u);  // previous window's transposed conv has read bufA
         const int seg = idx / p.max_win, win = idx - seg * p.max_win;
         const int Lprev = seg_rows(seg) / p.scale * p.prev_scale;
         const long long base_prev = (long long)p.seg_off[seg] * p.prev_scale;
@@ -249,7 +339,7 @@ __global__ void __maxnreg__(96) dec_planes_kernel(DecFusedParams p) {
 #pragma unroll
             for (int pp = 0; pp < 2; ++pp) {
               const uint64_t ad = a_tmpl | uint64_t(a0[pp] + uint32_t(ks * 2 * rows_in));
-              tc::mma_f16_ss(tmem + dcol + uint32_t((p0 + pp) * N), ad, bd, idesc, ks > 0 ? 1u : acc);
+              if (DEC3_KO != 1) tc::mma_f16_ss(tmem + dcol + uint32_t((p0 + pp) * N), ad, bd, idesc, ks > 0 ? 1u : acc);
             }
           }
         }
@@ -265,8 +355,28 @@ __global__ void __maxnreg__(96) dec_planes_kernel(DecFusedParams p) {
           for (int ks = 0; ks < 4; ++ks) {
             const uint64_t ad = a_tmpl | uint64_t(abase + uint32_t(1 - d + ks * 2 * g.rows_a));
             const uint64_t bd = b_tmpl | uint64_t(bbase + uint32_t((d * CHI + ks * 2) * NUP));
-            tc::mma_f16_ss(tmem + kT0, ad, bd, idU, (d || ks) ? 1u : 0u);
+            if (DEC3_KO != 1) tc::mma_f16_ss(tmem + kT0, ad, bd, idU, (d || ks) ? 1u : 0u);
           }
+      };
+      // conv_post: five (row shift, input plane) groups per issuer into its own 16-column tile of S
+      auto issue_post = [&] {
+        const uint64_t a_tmpl = tc::make_desc(0u, uint32_t(g.rows_yb) * 16u, 128u);
+        const uint64_t b_tmpl = tc::make_desc(0u, 16u * 16u, 128u);
+        const uint32_t abase = (tc::smem_u32(bufYB) >> 4) + uint32_t(g.hb);
+        const uint32_t bbase = wbase16 + (p.post.woff >> 4);
+        const uint32_t dcol = tmem + kS0 + (isA ? 0u : 16u);
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+          const int pair = (isA ? 0 : 5) + k;          // order: sh = -1: pi 1..3 | sh = 0: pi 0..3 | sh = +1: pi 0..2
+          const int sh = pair < 3 ? -1 : (pair < 7 ? 0 : 1);
+          const int pi = pair < 3 ? pair + 1 : (pair < 7 ? pair - 3 : pair - 7);
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks) {
+            const uint64_t ad = a_tmpl | uint64_t(abase + uint32_t(pi * g.pb + sh + ks * 2 * g.rows_yb));
+            const uint64_t bd = b_tmpl | uint64_t(bbase + uint32_t(pair * 64 + ks * 32));
+            if (DEC3_KO != 1) tc::mma_f16_ss(dcol, ad, bd, idP, (k || ks) ? 1u : 0u);
+          }
+        }
       };
       long long c_x = 0, c_y = 0, c_o = 0, c_s = 0;
       tc::mbar_wait(&bars[W_FULL], 0u);
@@ -290,7 +400,7 @@ __global__ void __maxnreg__(96) dec_planes_kernel(DecFusedParams p) {
         if (it > 0) {  // previous window's conv_post: its operand was published while c1_0 / c1_1 were being issued
           timed_wait(&bars[O_READY], ppar, c_o);
           tc::fence_after_sync();
-          conv(bufYB, g.rows_yb, g.pb, g.hb, p.post, 16, kS0, idP, false);
+          issue_post();
           tc::mma_commit(&bars[P_DONE]);
         }
         conv(bufX, g.rows_x, g.px, g.hx, p.c1[2], kC, kT0 + 256u, idC, false);
@@ -317,7 +427,7 @@ __global__ void __maxnreg__(96) dec_planes_kernel(DecFusedParams p) {
       }
       timed_wait(&bars[O_READY], uint32_t(it - 1) & 1u, c_o);
       tc::fence_after_sync();
-      conv(bufYB, g.rows_yb, g.pb, g.hb, p.post, 16, kS0, idP, false);
+      issue_post();
       tc::mma_commit(&bars[P_DONE]);
       if (prof && isA) {
         unsigned long long* q = reinterpret_cast<unsigned long long*>(p.prof);
@@ -339,16 +449,43 @@ __global__ void __maxnreg__(96) dec_planes_kernel(DecFusedParams p) {
     // x (fp32) and sum_j x1_j.  The running sum is kept as packed fp16 pairs (added in fp32, rounded once per chain): its
     // only consumer rounds (sum + S) / 3 to a 16-bit conv_post operand anyway, and 64 fp32 registers of per-thread state
     // do not fit next to the epilogue temporaries at 96 registers per thread.
-    float xr[kNP][8];
-    uint32_t xs[kNP][4];
+    unsigned long long xr[kNP][4];  // fp32 pairs
+    uint32_t xs[kNP][4];            // fp16 pairs
+    using u64 = unsigned long long;
+    const u64 slope01 = pk64(0.1f, 0.1f);
 
     auto store_op = [&](uint8_t* buf, int rows_total, int row, const uint32_t* pk) {
       *reinterpret_cast<uint4*>(buf + (size_t(cg) * rows_total + row) * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     };
-    auto load_bias = [&](int j, float* b) {
-      const float4 f0 = *reinterpret_cast<const float4*>(&sbias[j][col0]);
-      const float4 f1 = *reinterpret_cast<const float4*>(&sbias[j][col0 + 4]);
-      b[0] = f0.x, b[1] = f0.y, b[2] = f0.z, b[3] = f0.w, b[4] = f1.x, b[5] = f1.y, b[6] = f1.z, b[7] = f1.w;
+    auto load_bias = [&](int j, u64* b) {  // 8 channels = 4 pairs
+      const ulonglong2 f0 = *reinterpret_cast<const ulonglong2*>(&sbias[j][col0]);
+      const ulonglong2 f1 = *reinterpret_cast<const ulonglong2*>(&sbias[j][col0 + 4]);
+      b[0] = f0.x, b[1] = f0.y, b[2] = f1.x, b[3] = f1.y;
+    };
+    // one pass over the thread's four plane rows: DEC3_BATCH accumulator tiles per tcgen05.wait::ld, body(ph, pairs)
+    auto for_planes = [&](uint32_t tcol, auto&& body) {
+#pragma unroll
+      for (int pq = 0; pq < kNP; pq += DEC3_BATCH) {
+        float v[DEC3_BATCH][8];
+        if (DEC3_KO != 2) {
+#pragma unroll
+          for (int h = 0; h < DEC3_BATCH; ++h) tc::tmem_ld8(lane_base + tcol + uint32_t((pq + h) * kC), v[h]);
+          tc::tmem_ld_wait();
+        }
+#pragma unroll
+        for (int h = 0; h < DEC3_BATCH; ++h) {
+          if (DEC3_KO >= 2) {  // knock-out: publish something, skip the arithmetic
+            const uint32_t z[4] = {DEC3_KO == 3 ? __float_as_uint(v[h][0]) : 0u, 0u, 0u, 0u};
+            if (tcol == kT0) store_op(bufX, g.rows_x, (pq + h) * g.px + g.hx + tp, z);
+            else store_op(bufYB, g.rows_yb, (pq + h) * g.pb + g.hb + tp, z);
+            continue;
+          }
+          u64 a[4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) a[c] = pk64(v[h][2 * c], v[h][2 * c + 1]);
+          body(pq + h, a);
+        }
+      }
     };
     auto arrive = [&](int b) {
       tc::fence_async_smem();
@@ -361,35 +498,34 @@ __global__ void __maxnreg__(96) dec_planes_kernel(DecFusedParams p) {
 
     // transposed-conv epilogue of a window: x = D + b stays in registers, lrelu(x) becomes the first convs' operand
     auto up_epi = [&](int w0, int L, uint32_t par) {
-      timed_wait(&bars[U_DONE], par, e_u);
+      warp_wait(&bars[U_DONE], par, e_u);
       tc::fence_after_sync();
-#pragma unroll
-      for (int ph = 0; ph < kNP; ++ph) tc::tmem_ld8(lane_base + kT0 + uint32_t(ph * kC), xr[ph]);
-      tc::tmem_ld_wait();
-      float ub[8];
+      u64 ub[4];
       load_bias(0, ub);
-#pragma unroll
-      for (int ph = 0; ph < kNP; ++ph) {
+      for_planes(kT0, [&](int ph, const u64* a) {
         const int gi = w0 + u * tp + ph;
         const bool inside = gi >= 0 && gi < L;
         uint32_t pk[4];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) xr[ph][c] += ub[c];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) pk[c] = inside ? E::pack2(lrelu(xr[ph][2 * c], 0.1f), lrelu(xr[ph][2 * c + 1], 0.1f)) : 0u;
+        for (int c = 0; c < 4; ++c) {
+          xr[ph][c] = add2(a[c], ub[c]);
+          pk[c] = inside ? lrelu_op<E, FMT>(xr[ph][c], slope01, 0.1f) : 0u;
+        }
         store_op(bufX, g.rows_x, ph * g.px + g.hx + tp, pk);
-      }
+      });
       arrive(X_READY);
     };
-    // conv_post result of a window: column 0 of each plane's 16-column block, tanh, store, per-utterance peak
+    // conv_post result of a window: the row's four samples, tanh, store, per-utterance peak
     auto post_epi = [&](int seg, int w0, int L, long long base, uint32_t par) {
-      timed_wait(&bars[P_DONE], par, e_p);  // every warp: YB may be rewritten once conv_post has read it
+      warp_wait(&bars[P_DONE], par, e_p);  // every warp: YB may be rewritten once conv_post has read it
       if (cg == 0) {
         tc::fence_after_sync();
-        float v[kNP];
-#pragma unroll
-        for (int ph = 0; ph < kNP; ++ph) v[ph] = tc::tmem_ld1(lane_base + kS0 + uint32_t(ph * 16));
+        float v[kNP], v2[kNP];
+        tc::tmem_ld4(lane_base + kS0, v);        // issuer A's groups: column ph' = sample 4t + ph'
+        tc::tmem_ld4(lane_base + kS0 + 16u, v2);  // issuer B's groups
         tc::tmem_ld_wait();
+#pragma unroll
+        for (int ph = 0; ph < kNP; ++ph) v[ph] += v2[ph];
         float mx = 0.f;
 #pragma unroll
         for (int ph = 0; ph < kNP; ++ph) {
@@ -428,35 +564,45 @@ __global__ void __maxnreg__(96) dec_planes_kernel(DecFusedParams p) {
       // ---- first conv of each chain: x1 = x + b + conv(lrelu x); operand of the second conv = lrelu(x1) ----
 #pragma unroll 1
       for (int j = 0; j < 3; ++j) {
-        timed_wait(&bars[C1_DONE + j], par, e_c1);
+        warp_wait(&bars[C1_DONE + j], par, e_c1);
         if (j == 1 && it > 0) post_epi(pseg, pw0, pL, pbase, par ^ 1u);  // previous window's audio; frees S and YB
-        if (j == 2) timed_wait(&bars[YA_FREE], par, e_c2);                // chain 0's second conv has read YA
+        if (j == 2) warp_wait(&bars[YA_FREE], par, e_c2);                // chain 0's second conv has read YA
         tc::fence_after_sync();
         uint8_t* const by = j == 1 ? bufYB : bufYA;
         const int rows_t = j == 1 ? g.rows_yb : g.rows_ya, pitch = j == 1 ? g.pb : g.pa, hy = j == 1 ? g.hb : g.ha;
-        float bj[8];
+        u64 bj[4];
         load_bias(1 + j, bj);
-#pragma unroll
-        for (int ph = 0; ph < kNP; ++ph) {
-          float v[8];
-          tc::tmem_ld8(lane_base + kT0 + uint32_t(j * 128 + ph * kC), v);
-          tc::tmem_ld_wait();
+        for_planes(kT0 + uint32_t(j * 128), [&](int ph, const u64* a) {
           const int gi = w0 + u * tp + ph;
           const bool inside = gi >= 0 && gi < L;
           uint32_t pk[4];
 #pragma unroll
-          for (int c = 0; c < 8; ++c) v[c] += xr[ph][c] + bj[c];
-#pragma unroll
           for (int c = 0; c < 4; ++c) {
-            float2 f = make_float2(0.f, 0.f);
-            if (j > 0) f = __half22float2(*reinterpret_cast<const __half2*>(&xs[ph][c]));
-            const __half2 h = __floats2half2_rn(f.x + v[2 * c], f.y + v[2 * c + 1]);
-            xs[ph][c] = *reinterpret_cast<const uint32_t*>(&h);
+            const u64 v = add2(add2(a[c], xr[ph][c]), bj[c]);  // x1 = conv + x + b
+            float v0, v1;
+            un64(v, v0, v1);
+            if constexpr (DEC3_H2 && FMT == 0) {
+              const uint32_t pv = E::pack2(v0, v1);
+              if (j > 0) {
+                const __half2 h = __hadd2(*reinterpret_cast<const __half2*>(&xs[ph][c]), *reinterpret_cast<const __half2*>(&pv));
+                xs[ph][c] = *reinterpret_cast<const uint32_t*>(&h);
+              } else {
+                xs[ph][c] = pv;
+              }
+              pk[c] = inside ? E::lrelu2(pv, 0.1f) : 0u;
+            } else {
+              float s0 = 0.f, s1 = 0.f;
+              if (j > 0) {
+                const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&xs[ph][c]));
+                s0 = f.x, s1 = f.y;
+              }
+              const __half2 h = __floats2half2_rn(s0 + v0, s1 + v1);
+              xs[ph][c] = *reinterpret_cast<const uint32_t*>(&h);
+              pk[c] = inside ? lrelu_pack<E>(v, slope01) : 0u;
+            }
           }
-#pragma unroll
-          for (int c = 0; c < 4; ++c) pk[c] = inside ? E::pack2(lrelu(v[2 * c], 0.1f), lrelu(v[2 * c + 1], 0.1f)) : 0u;
           store_op(by, rows_t, ph * pitch + hy + tp, pk);
-        }
+        });
         arrive(Y_READY + j);
       }
 
@@ -467,29 +613,24 @@ __global__ void __maxnreg__(96) dec_planes_kernel(DecFusedParams p) {
       }
 
       // ---- out = (sum_j x1_j + S + late bias) / 3; operand of conv_post = lrelu(out, 0.01) in YB ----
-      timed_wait(&bars[C2_DONE], par, e_f);
+      warp_wait(&bars[C2_DONE], par, e_f);
       tc::fence_after_sync();
       {
-        float bl[8];
+        u64 bl[4];
         load_bias(4, bl);
-#pragma unroll
-        for (int ph = 0; ph < kNP; ++ph) {
-          float v[8];
-          tc::tmem_ld8(lane_base + kS0 + uint32_t(ph * kC), v);
-          tc::tmem_ld_wait();
+        const u64 inv2 = pk64(p.inv_nk, p.inv_nk), slope001 = pk64(0.01f, 0.01f);
+        for_planes(kS0, [&](int ph, const u64* a) {
           const int gi = w0 + u * tp + ph;
           const bool inside = gi >= 0 && gi < L;
           uint32_t pk[4];
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&xs[ph][c]));
-            v[2 * c] = lrelu((v[2 * c] + f.x + bl[2 * c]) * p.inv_nk, 0.01f);
-            v[2 * c + 1] = lrelu((v[2 * c + 1] + f.y + bl[2 * c + 1]) * p.inv_nk, 0.01f);
+            const u64 o = mul2(add2(add2(a[c], pk64(f.x, f.y)), bl[c]), inv2);
+            pk[c] = inside ? lrelu_op<E, FMT>(o, slope001, 0.01f) : 0u;
           }
-#pragma unroll
-          for (int c = 0; c < 4; ++c) pk[c] = inside ? E::pack2(v[2 * c], v[2 * c + 1]) : 0u;
           store_op(bufYB, g.rows_yb, ph * g.pb + g.hb + tp, pk);
-        }
+        });
       }
       arrive(O_READY);
       pseg = seg;

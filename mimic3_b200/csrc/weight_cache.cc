@@ -19,7 +19,7 @@ namespace {
 // ---- tripwires: a field added to one of these structs must also be added to its io() below (and
 // kCacheLayoutVersion bumped); the sizes are those of the one platform this library is built for (x86-64 Linux).
 static_assert(sizeof(TcConvW) == 40 && sizeof(RowTcW) == 24 && sizeof(Lin) == 96, "update io(Lin) + layout version");
-static_assert(sizeof(FlowTcW) == 80 && sizeof(MrfStageW) == 104 && sizeof(DecLastW) == 88, "update io() + version");
+static_assert(sizeof(FlowTcW) == 80 && sizeof(MrfStageW) == 104 && sizeof(DecLastW) == 96, "update io() + version");
 static_assert(sizeof(UpW) == 80 && sizeof(DDSW) == 432 && sizeof(EncLayerW) == 432, "update io() + layout version");
 
 struct Writer {
@@ -217,11 +217,12 @@ void io(Ar& a, MrfStageW& m) {
 template <typename Ar>
 void io(Ar& a, DecLastW& d) {
   a.pod(d.ok); a.pod(d.up_woff); a.pod(d.post_woff); a.pod(d.fused_ok); a.pod(d.planes_ok); a.pod(d.blob_off); a.pod(d.blob_bytes);
-  a.pod(d.f_up); a.pod(d.f_post);
+  a.pod(d.f_up); a.pod(d.f_post); a.pod(d.f_postp);
   for (int i = 0; i < 3; ++i) { a.pod(d.f_c1[i]); a.pod(d.f_c2[i]); a.pod(d.HYb[i]); }
   check_woff(a, d.up_woff);
   check_woff(a, d.post_woff);
   check_woff(a, d.blob_off + (d.blob_bytes + 1) / 2);
+  if (d.planes_ok) check_woff(a, d.blob_off + (d.f_postp + kDecPostPlanesBytes + 1) / 2);
 }
 template <typename Ar, typename T>
 void io_vec(Ar& a, std::vector<T>& v) {

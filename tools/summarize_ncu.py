@@ -3,6 +3,8 @@
 
     python tools/summarize_ncu.py launches gpurun_out/r01b_launches.csv [--last-step N] > profiles/..._launches.md
     python tools/summarize_ncu.py full gpurun_out/r01b_full_raw.csv > profiles/..._ncu_full.md
+    python tools/summarize_ncu.py traffic gpurun_out/r02s_full_raw.csv <samples of that launch> <source label>
+        -> updates profiles/traffic.json (DRAM bytes per audio sample of each captured kernel; bench.py's roofline.traffic)
 """
 import collections
 import csv
@@ -96,8 +98,34 @@ def full(path):
         print(f"| {short(row[idx['Kernel Name']])} | {row[idx['Grid Size']]} | " + " | ".join(cells) + " |")
 
 
+def traffic(path, samples, source):
+    import json
+    import pathlib
+    with open(path) as f:
+        lines = [l for l in f if not l.startswith("==")]
+    rd = csv.reader(lines)
+    header = next(rd)
+    units = next(rd)
+    idx = {h: i for i, h in enumerate(header)}
+    out_path = pathlib.Path(__file__).resolve().parent.parent / "profiles" / "traffic.json"
+    table = json.loads(out_path.read_text()) if out_path.exists() else {}
+    for row in rd:
+        if not row:
+            continue
+        name = re.sub(r"<.*$", "", short(row[idx["Kernel Name"]]))
+        rdb = to_bytes(row[idx["dram__bytes_read.sum"]], units[idx["dram__bytes_read.sum"]])
+        wrb = to_bytes(row[idx["dram__bytes_write.sum"]], units[idx["dram__bytes_write.sum"]])
+        table[name] = {"dram_bytes_per_sample": (rdb + wrb) / samples, "dram_read_bytes": rdb, "dram_write_bytes": wrb,
+                       "samples_in_launch": samples, "source": source}
+        print(name, table[name])
+    out_path.write_text(json.dumps(table, indent=1, sort_keys=True) + "\n")
+
+
 if __name__ == "__main__":
     mode, path = sys.argv[1], sys.argv[2]
+    if mode == "traffic":
+        traffic(path, float(sys.argv[3]), sys.argv[4])
+        sys.exit(0)
     if mode == "launches":
         n = int(sys.argv[4]) if len(sys.argv) > 4 and sys.argv[3] == "--last-step" else None
         launches(path, n)
