@@ -617,7 +617,10 @@ def main():
                          "note": "smem operand fetch caps SS-mode MMAs at N=32 to 40 % of the tensor peak (DESIGN.md §3)"},
             "e2e": {"value": tot_e2e / e2e_max, "unit": "samples/s",
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(tot_e2e / args.steps * 2),
-                    "ms_per_step": e2e_max / args.steps * 1e3},
+                    "ms_per_step": e2e_max / args.steps * 1e3,
+                    "note": (None if distributed or args.e2e_depth <= 1 else
+                             f"{args.e2e_depth} m3_infer calls in flight: call k+1's kernels also fill the tails of call k's persistent kernels and "
+                             "the host round trip of the duration predictor, so this can exceed `value`, which times one call at a time")},
             "gpu_launches": int(tot_launch),
             "clocks": clocks,
             "reference_probe": probe_reference_stack(),

@@ -1,7 +1,7 @@
 #!/bin/bash
 # r02w: evidence after dec_planes_kernel: full GPU suite, bench line (cfg3 with CPU leg; cfg2/4/5), launch list, ncu --set full
 # of the last-stage kernel, per-role cycle counters (profile build)
-OUT=gpurun_out; mkdir -p $OUT; T=${TAG:-r02w}
+OUT=gpurun_out; mkdir -p $OUT; T=${TAG:-r03b}
 ( time timeout 700 python -m pytest tests -m gpu -x -q -s ) > $OUT/${T}_pytest.log 2>&1
 echo "pytest exit $?" >> $OUT/${T}_pytest.log; grep -E "passed|failed|rror" $OUT/${T}_pytest.log | tail -3
 timeout 400 python bench.py --steps 20 --warmup 3 > $OUT/${T}_bench_cfg3.json 2> $OUT/${T}_bench_cfg3.err; echo "cfg3 exit $?"
