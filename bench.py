@@ -414,11 +414,31 @@ def main():
         max_rows = max(j["ids"].shape[0] for j in jobs)
         max_t = max(j["T"] for j in jobs)
         per = (max_rows + world - 1) // world
-        scat = IdScatter(max_rows, max_t, dev, payload_group=None, meta_group=meta_pg)
-        # capacity: generous bound per rank (ids x 12 frames/id x hop); the synthetic voices give 4-5 frames per id
-        cap = per * max_t * 12 * 256
-        if args.gather == "host":
-            coll = HostPcmCollector(cap, per, dev, meta_group=meta_pg, depth=max(1, args.e2e_depth))
+        # two scatter buffer sets: the ids of call k+1 are scattered while call k runs
+        scats = [IdScatter(max_rows, max_t, dev, payload_group=None, meta_group=meta_pg) for _ in range(2)]
+        scat = scats[0]
+        # capacity per rank: ids x 7 frames/id x hop (the synthetic voices give 4.2-4.7 frames per id; the whole segment is pinned,
+        # so a looser bound costs real /dev/shm pages: world x depth x cap x 2 bytes)
+        cap = per * max_t * 7 * 256
+        gather = args.gather
+        if gather == "host":  # the shared segment must fit /dev/shm (a tmpfs that is too small kills the process with SIGBUS)
+            ok = [True]
+            if rank == 0:
+                try:
+                    st = os.statvfs("/dev/shm")
+                    need = 2 * cap * world * max(3, args.e2e_depth)
+                    ok[0] = st.f_bavail * st.f_frsize > need + (64 << 20)
+                    if not ok[0]:
+                        print(f"[bench] /dev/shm has {st.f_bavail * st.f_frsize >> 20} MiB free, the PCM segment needs {need >> 20} MiB: "
+                              "falling back to the NCCL gather", file=sys.stderr, flush=True)
+                except OSError:
+                    ok[0] = False
+            dist.broadcast_object_list(ok, src=0, group=meta_pg)
+            if not ok[0]:
+                gather = "nccl"
+        args.gather = gather
+        if gather == "host":  # two engine calls in flight per rank (below) + one copy in flight: three slots
+            coll = HostPcmCollector(cap, per, dev, meta_group=meta_pg, depth=max(3, args.e2e_depth))
         else:
             coll = PcmCollector(cap, per, dev, payload_group=gather_pg, meta_group=meta_pg, depth=max(1, args.e2e_depth))
     tickets = deque()
@@ -445,6 +465,16 @@ def main():
         r.close()
         return n
 
+    dpool = ThreadPoolExecutor(max_workers=2) if distributed else None
+    dstate = {"next": None, "k": 0}
+    inflight = deque()
+
+    def do_scatter(ji):
+        jj = jobs[ji]
+        sc = scats[dstate["k"] & 1]
+        dstate["k"] += 1
+        return sc(jj["ids"] if rank == 0 else None, jj["lengths"] if rank == 0 else None, jj["sid"] if rank == 0 else None)
+
     def step_e2e(seed):
         """N=1: `m3_infer` with host ids, PCM lands in pinned host memory.  N>1: rank 0 owns the host buffers."""
         n = 0
@@ -457,33 +487,55 @@ def main():
                     while len(tickets) >= args.e2e_depth:
                         n += tickets.popleft().result()
                 continue
+            # N>1, pipelined like N=1: up to two engine calls of this rank in flight in worker threads (the C library releases
+            # the GIL; call k+1's kernels fill the tails of call k's persistent kernels), while this thread submits the PCM of
+            # the call that just finished (D2H into the shared segment), finishes the one before (wait for its copy, host-side
+            # gather of the counts, barrier) and scatters the ids of the next call into the other buffer set.  All collectives
+            # stay on this thread, in the same order on every rank.  (The NCCL gather keeps one call in flight.)
             ta = time.perf_counter()
-            d_ids, lens, sids = scat(j["ids"] if rank == 0 else None, j["lengths"] if rank == 0 else None,
-                                     j["sid"] if rank == 0 else None)
-            buf = coll.send_buffer()
+            ji = jobs.index(j)
+            if dstate["next"] is None:
+                dstate["next"] = do_scatter(ji)
+            d_ids, lens, sids = dstate["next"]
+            two = args.gather == "host"
+            buf = coll.send_buffer(len(inflight)) if two else coll.send_buffer()
             tb = time.perf_counter()
             if len(lens):
-                r = j["sess"].infer(d_ids.stride(0), lens, j["scales"], sids, seed=seed, host_copy=False,
-                                    device_ids_ptr=d_ids.data_ptr(), device_pcm_out=buf)
-                tc_ = time.perf_counter()
-                tickets.append(coll.submit(r.total_samples, r.frames))
+                inflight.append(dpool.submit(j["sess"].infer, d_ids.stride(0), lens, j["scales"], sids, seed=seed, host_copy=False,
+                                             device_ids_ptr=d_ids.data_ptr(), device_pcm_out=buf))
             else:
-                tc_ = time.perf_counter()
-                tickets.append(coll.submit(0, []))
+                inflight.append(None)
+            tc_ = time.perf_counter()
+            while len(inflight) > (1 if two else 0):   # the older call: its PCM is final, start its copy
+                f = inflight.popleft()
+                if f is not None:
+                    r = f.result()
+                    tickets.append(coll.submit(r.total_samples, r.frames))
+                else:
+                    tickets.append(coll.submit(0, []))
             td = time.perf_counter()
-            while len(tickets) >= max(1, args.e2e_depth):
+            while len(tickets) >= 2:
                 n += e2e_collect(tickets.popleft())
+            te = time.perf_counter()
+            dstate["next"] = do_scatter((ji + 1) % len(jobs))   # (the last one of the run is never used)
             if trace is not None:
-                te = time.perf_counter()
-                trace["scatter"] += tb - ta
-                trace["infer"] += tc_ - tb
-                trace["submit"] += td - tc_
+                tf = time.perf_counter()
+                trace["scatter"] += (tb - ta) + (tf - te)
+                trace["infer"] += td - tc_
+                trace["submit"] += 0.0
                 trace["collect"] += te - td
                 trace["n"] += 1
         return n
 
     def e2e_drain():
         n = 0
+        while distributed and inflight:
+            f = inflight.popleft()
+            if f is not None:
+                r = f.result()
+                tickets.append(coll.submit(r.total_samples, r.frames))
+            else:
+                tickets.append(coll.submit(0, []))
         while tickets:
             t = tickets.popleft()
             n += t.result() if pool is not None else e2e_collect(t)
@@ -599,7 +651,7 @@ def main():
                        "l2": "no flush: per-step activations (GBs) exceed the 126 MB L2 many times over",
                        "timing": "wall clock between barrier+synchronize pairs (>= CUDA-event time), max over ranks",
                        "device_event_ms_per_step": dev_max / args.steps * 1e3,
-                       "e2e_pipeline": ((f"N>1: id scatter (pinned H2D + NCCL) every step; PCM: every rank copies its own int16 PCM over its own "
+                       "e2e_pipeline": ((f"N>1: id scatter (pinned H2D + NCCL) every step, two engine calls per rank in flight in worker threads, ids of call k+1 scattered meanwhile; PCM: every rank copies its own int16 PCM over its own "
                                          f"PCIe link into its slice of ONE shared pinned host segment that rank 0 reads (no payload collective), "
                                          f"{max(1, args.e2e_depth)} slots: step k's copies overlap step k+1's compute"
                                          if args.gather == "host" else

@@ -293,8 +293,11 @@ class HostPcmCollector:
     def _slot(self) -> int:
         return self.k % self.depth
 
-    def send_buffer(self):
-        s = self._slot()
+    def send_buffer(self, ahead: int = 0):
+        """Device buffer of the next call's PCM.  ``ahead`` = engine calls that already hold a buffer but have not been
+        ``submit``-ted yet (two calls in flight: the second one asks with ``ahead=1``); needs ``depth >= ahead + 2`` for
+        the slot's previous copy to be long finished."""
+        s = (self.k + ahead) % self.depth
         t = self.pending[s]
         if t is not None:          # the slot's previous D2H must have left the device buffer
             if t.event is not None:
