@@ -118,3 +118,68 @@ def test_host_segment_collector_world3_gloo(tmp_path):
     port = 33500 + (os.getpid() % 2000)
     mp.spawn(_worker, args=(3, port, str(tmp_path), "host"), nprocs=3, join=True)
     assert (tmp_path / "ok").exists()
+
+
+def _worker_two_in_flight(rank, world, port, tmp):
+    """The bench's N>1 loop: two 'engine calls' per rank hold send buffers at once (the second one taken with ahead=1),
+    three collector slots, two id-scatter buffer sets, collect two submits behind."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, str(ROOT))
+    import torch.distributed as dist
+    from mimic3_b200.shard import HostPcmCollector, IdScatter, make_groups, shard_bounds
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    pg, mg = make_groups("cpu")
+    T, per = 11, (9 + world - 1) // world
+    scats = [IdScatter(max_rows=9, max_t=16, device="cpu", payload_group=pg, meta_group=mg) for _ in range(2)]
+    coll = HostPcmCollector(capacity_samples=per * 16 * 4, max_rows_per_rank=per, device="cpu", meta_group=mg, depth=3)
+
+    def batch(step):
+        rng = np.random.default_rng(100 + step)
+        Bs = [7, 5, 2, 9, 1, 7, 3][step]
+        return (rng.integers(4, 50, size=(Bs, T)).astype(np.int64), rng.integers(1, T + 1, size=Bs).astype(np.int64))
+
+    def scatter(step):
+        ids, lengths = batch(step)
+        return scats[step & 1](ids if rank == 0 else None, lengths if rank == 0 else None, None)
+
+    def synth(buf, shard, step):      # the stand-in engine call: fills ITS buffer, possibly long after a later call took the next one
+        n, frames = 0, []
+        for i in range(shard[0].shape[0]):
+            k = int(shard[1][i]) * 4
+            buf[n:n + k] = int(shard[0][i, 0]) + step
+            n += k
+            frames.append(int(shard[1][i]))
+        return n, frames
+
+    steps, inflight, tickets, want = 7, [], [], []
+    nxt = scatter(0)
+    for step in range(steps):
+        shard = nxt
+        buf = coll.send_buffer(len(inflight))          # 0 or 1 calls already hold a buffer
+        inflight.append((buf, (shard[0].clone(), shard[1].copy()), step))
+        if len(inflight) > 1:                          # the older call "finishes" only now, after the newer one took its buffer
+            b, sh, st = inflight.pop(0)
+            tickets.append(coll.submit(*synth(b, sh, st)))
+            want.append(batch(st) + (st,))
+        while len(tickets) >= 2:
+            _check(coll.collect(tickets.pop(0)), want.pop(0), rank, world)
+        if step + 1 < steps:
+            nxt = scatter(step + 1)                    # into the other buffer set, while `shard`'s call is still "running"
+    while inflight:
+        b, sh, st = inflight.pop(0)
+        tickets.append(coll.submit(*synth(b, sh, st)))
+        want.append(batch(st) + (st,))
+    while tickets:
+        _check(coll.collect(tickets.pop(0)), want.pop(0), rank, world)
+    coll.drain()
+    coll.close()
+    if rank == 0:
+        Path(tmp, "ok").write_text("ok")
+    dist.destroy_process_group()
+
+
+def test_two_calls_in_flight_world2_gloo(tmp_path):
+    import torch.multiprocessing as mp
+    port = 35500 + (os.getpid() % 2000)
+    mp.spawn(_worker_two_in_flight, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "ok").exists()
