@@ -204,30 +204,51 @@ class B200UtteranceQueue:
                 rows.append(None)
         return rows
 
-    def end_utterance(self) -> typing.Iterable[typing.Any]:
+    def end_utterance(self, max_batch_sentences: typing.Optional[int] = None) -> typing.Iterable[typing.Any]:
         """Same results in the same order as ``tts.py:470-515``; one engine call per voice instead of one per
-        sentence.  (A generator like the reference's: nothing runs until it is iterated.)"""
+        sentence.  (A generator like the reference's: nothing runs until it is iterated.)
+
+        ``max_batch_sentences`` bounds how many sentences are synthesised before anything is yielded: the plan is cut
+        into groups of at most that many sentences (marks and breaks stay with the sentence they follow), each
+        group is one engine call per voice, and its results are yielded before the next group runs.  ``None`` (default)
+        = the whole utterance in one batch (highest throughput); ``1`` = the reference's behaviour, one sentence per
+        yield with ``self.settings`` / ``self.voice`` read when that sentence is spoken (lowest first-audio latency)."""
+        if max_batch_sentences is not None and max_batch_sentences < 1:
+            raise ValueError("max_batch_sentences must be >= 1")
         plan = plan_sentences(self._results)
-        rows = self._rows(plan)
-        by_voice: typing.Dict[str, typing.List[int]] = {}
-        for i, row in enumerate(rows):
-            if row is not None:
-                by_voice.setdefault(row[0], []).append(i)
-        audio: typing.Dict[int, np.ndarray] = {}
-        for key, idxs in by_voice.items():
-            voice = rows[idxs[0]][1]
-            st = [rows[i][3] for i in idxs]
-            outs = voice.ids_to_audio_rows(
-                [rows[i][2] for i in idxs], speakers=[s.speaker for s in st], length_scales=[s.length_scale for s in st],
-                noise_scales=[s.noise_scale for s in st], noise_ws=[s.noise_w for s in st], rates=[s.rate for s in st],
-                volumes=[s.volume for s in st])
-            audio.update(zip(idxs, outs))
-        for i, item in enumerate(plan):
-            if rows[i] is None:
-                yield item
-            else:
-                yield AudioResult(sample_rate_hz=rows[i][1].config.audio.sample_rate, audio_bytes=audio[i].tobytes(),
-                                  sample_width_bytes=2, num_channels=1)
+        start = 0
+        while start < len(plan) or start == 0:
+            stop, n = start, 0
+            while stop < len(plan):          # extend the group up to the sentence budget (+ trailing marks / breaks)
+                if isinstance(plan[stop], _Sentence):
+                    if max_batch_sentences is not None and n == max_batch_sentences:
+                        break
+                    n += 1
+                stop += 1
+            group = plan[start:stop]
+            rows = self._rows(group)         # settings / voice are read here, i.e. when this group is spoken
+            by_voice: typing.Dict[str, typing.List[int]] = {}
+            for i, row in enumerate(rows):
+                if row is not None:
+                    by_voice.setdefault(row[0], []).append(i)
+            audio: typing.Dict[int, np.ndarray] = {}
+            for key, idxs in by_voice.items():
+                voice = rows[idxs[0]][1]
+                st = [rows[i][3] for i in idxs]
+                outs = voice.ids_to_audio_rows(
+                    [rows[i][2] for i in idxs], speakers=[s.speaker for s in st], length_scales=[s.length_scale for s in st],
+                    noise_scales=[s.noise_scale for s in st], noise_ws=[s.noise_w for s in st], rates=[s.rate for s in st],
+                    volumes=[s.volume for s in st])
+                audio.update(zip(idxs, outs))
+            for i, item in enumerate(group):
+                if rows[i] is None:
+                    yield item
+                else:
+                    yield AudioResult(sample_rate_hz=rows[i][1].config.audio.sample_rate, audio_bytes=audio[i].tobytes(),
+                                      sample_width_bytes=2, num_channels=1)
+            if stop >= len(plan):
+                break
+            start = stop
         self._results.clear()
 
     def end_utterance_wav(self) -> bytes:

@@ -251,7 +251,8 @@ def test_queue_results_match_reference_speak_sentence_goldens():
         e = case["end_settings"]
         q.settings = tts.B200Settings(voice=e["voice"], speaker=e["speaker"], length_scale=e["length_scale"],
                                       noise_scale=e["noise_scale"], noise_w=e["noise_w"], volume=e["volume"], rate=e["rate"])
-        got = list(q.end_utterance())
+        chunk = (None, 1, 2, 3)[cases.index(case) % 4]   # the streaming mode must yield the very same results
+        got = list(q.end_utterance(max_batch_sentences=chunk))
         assert len(got) == len(case["yielded"])
         for g, want in zip(got, case["yielded"]):
             if want["kind"] == "audio":
@@ -262,6 +263,43 @@ def test_queue_results_match_reference_speak_sentence_goldens():
             else:
                 assert isinstance(g, tts.MarkResult) and g.name == want["name"]
         assert sum(log) == len(case["calls"])                    # same sentences synthesised ...
-        assert len(log) == len({c["voice"] for c in case["calls"]})   # ... in ONE engine call per voice
-        n_calls += len(log)
-    assert n_audio > 250 and n_calls < 231
+        if chunk is None:
+            assert len(log) == len({c["voice"] for c in case["calls"]})   # ... in ONE engine call per voice
+            n_calls += len(log)
+        else:
+            assert max(log, default=0) <= chunk and len(log) <= len(case["calls"])
+    assert n_audio > 250 and n_calls < 80
+
+
+def test_streaming_end_utterance_is_lazy_and_reads_settings_per_group():
+    """max_batch_sentences=1 is the reference's generator (tts.py:470-515): a sentence is synthesised when the consumer asks
+    for it, with the settings in force at that moment for sentences that carry none of their own."""
+    calls = []
+
+    class V:
+        def __init__(self, key):
+            from types import SimpleNamespace
+            self.key = key
+            self.config = SimpleNamespace(audio=SimpleNamespace(sample_rate=22050))
+
+        def phonemes_to_ids(self, phonemes):
+            return [len(w) for w in phonemes]
+
+        def ids_to_audio_rows(self, batch_ids, speakers=None, length_scales=None, **kw):
+            calls.append((self.key, len(batch_ids), list(length_scales)))
+            return [np.full(4, len(ids), dtype=np.int16) for ids in batch_ids]
+
+    q = tts.B200UtteranceQueue(tts.B200Settings(voice="a"), lambda key: V(key))
+    for n in (1, 2, 3):
+        q._results.append(tts.B200Phonemes(current_settings=None, phonemes=[["x"] * n], is_utterance=True))
+        q.set_mark(f"m{n}")
+    gen = q.end_utterance(max_batch_sentences=1)
+    assert calls == []                                  # nothing runs until it is iterated
+    first = next(gen)
+    assert isinstance(first, tts.AudioResult) and len(calls) == 1 and calls[0][1] == 1
+    q.settings.length_scale = 2.5                       # changed while the utterance is being spoken
+    rest = list(gen)
+    assert [type(r).__name__ for r in [first] + rest] == ["AudioResult", "MarkResult"] * 3
+    assert len(calls) == 3 and calls[1][2] == [2.5] and calls[2][2] == [2.5]
+    assert q._results == []
+
